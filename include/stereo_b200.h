@@ -1,0 +1,120 @@
+/* stereo_b200.h -- C ABI of libstereo_b200.so, the sm_100a stereo-matching backend.
+ *
+ * Drop-in boundary for the reference's `cuda_depth` pybind module
+ * (reference: src/csrc/depth/torch_extension_module.cc:6-27) and the C++ class behind it
+ * (src/csrc/depth/stereo_matching.hh:8-34, stereo_matching.cc:17-43).  Plain pointers and
+ * sizes only; no torch types.  The Python shim stereo_depth_b200/cuda_depth.py binds these
+ * entry points with ctypes (see INTEGRATION.md for the reference-side stub).
+ *
+ * All image pointers of sd_compute are DEVICE pointers on the handle's device.
+ * All functions return SD_OK (0) or a negative sd_status; sd_last_error() gives the text.
+ * A handle is not thread-safe; distinct handles are independent.
+ */
+#ifndef STEREO_B200_H
+#define STEREO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SD_ABI_VERSION 1
+
+/* Replaces struct stereo_matching_configuration
+ * (src/csrc/depth/stereo_matching_configuration.hh:5-17); field order = the pybind ctor's
+ * argument order (torch_extension_module.cc:8-19). */
+typedef struct sd_config {
+    int32_t height;            /* 1080 */
+    int32_t width;             /* 1920 (the pybind default is 1980, torch_extension_module.cc:10) */
+    int32_t downscale_factor;  /* 2    K */
+    int32_t min_disparity;     /* 75 */
+    int32_t max_disparity;     /* 262 */
+    int32_t ncc_patch_radius;  /* 1    3x3 similarity cost on the pooled images */
+    int32_t sad_patch_radius;  /* 5    11x11 secondary matching on the full-res images */
+    int32_t threshold;         /* 5    bilateral-fill disparity threshold */
+    int32_t small_mbm_radius;  /* 1 */
+    int32_t mid_mbm_radius;    /* 4 */
+    int32_t large_mbm_radius;  /* 10 */
+} sd_config;
+
+typedef struct sd_handle sd_handle;
+
+typedef enum sd_status {
+    SD_OK = 0,
+    SD_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, radius ordering ... */
+    SD_ERR_SHAPE = -2,        /* n_frames / dtype / stage does not fit the handle */
+    SD_ERR_CUDA = -3,         /* a CUDA call failed; sd_last_cuda_error() holds the cudaError_t */
+    SD_ERR_NOMEM = -4,
+    SD_ERR_UNSUPPORTED = -5
+} sd_status;
+
+typedef enum sd_dtype { SD_U8 = 0, SD_F32 = 1 } sd_dtype;
+
+/* Intermediates kept in HBM for the LAST frame chunk processed (parity tests / debugging).
+ * Replaces nothing in the reference API: its device_buffer (buffer/device_buffer.hh:12-19) is private. */
+typedef enum sd_stage {
+    SD_STAGE_GRAY_L = 0,   /* float [H,W]    rgb_to_grayscale.cu:24-28 */
+    SD_STAGE_GRAY_R = 1,
+    SD_STAGE_POOL_L = 2,   /* float [Hd,Wd]  mean_pool.cu:25-35 */
+    SD_STAGE_POOL_R = 3,
+    SD_STAGE_WTA = 4,      /* float [Hd,Wd]  wta_disparity_selection.cu:22-30 (disparity incl. min_d/K) */
+    SD_STAGE_AGG3 = 5,     /* float [Hd,Wd,3] aggregated cost at d*-1, d*, d*+1 (circular), the three
+                              values secondary_matching.cu:55-58 reads from the aggregated volume */
+    SD_STAGE_REFINED = 6   /* float [Hd,Wd]  secondary_matching.cu:55-70 */
+} sd_stage;
+
+int sd_abi_version(void);
+
+/* Fills *cfg with the reference's defaults (stereo_matching_configuration.hh:6-16). */
+int sd_config_default(sd_config *cfg);
+
+/* Hd = ceil(H/K), Wd = ceil(W/K), L = max/K - min/K + 1 (buffer/device_buffer.cc:7-9). */
+int sd_dims(const sd_config *cfg, int32_t *Hd, int32_t *Wd, int32_t *L);
+
+/* Replaces stereo_matching::stereo_matching (stereo_matching.cc:17-20): validates the configuration
+ * and allocates all scratch for `frames_per_launch` frames on `device` (<=0 selects a default).
+ * Unlike the reference, no [Hd,Wd,L] cost volume is ever allocated. */
+int sd_create(const sd_config *cfg, int device, int frames_per_launch, sd_handle **out);
+int sd_destroy(sd_handle *h);
+
+/* Replaces stereo_matching::compute_disparity_map (stereo_matching.cc:22-43) for a batch:
+ * left/right: [n_frames,3,H,W] CHW, uint8 or float32 (values as the reference sees them after
+ * `.float()`), contiguous, device memory.  out: float32 [n_frames,H,W] device memory.
+ * Asynchronous on `cuda_stream` (a cudaStream_t; NULL = legacy default stream, which is the
+ * stream the reference launches on).  No allocation, no host synchronisation. */
+int sd_compute(sd_handle *h, const void *left, const void *right, int dtype, int n_frames,
+               float *out, void *cuda_stream);
+
+/* Same computation with HOST buffers (pinned memory recommended): host->device copies, the
+ * kernels and device->host copies are pipelined over internal streams, chunk by chunk.
+ * Synchronous: returns when `out` is complete.  This is the end-to-end call
+ * CudaStereoMatchingBackend.process makes for CPU tensors
+ * (src/python/pipeline/depth/cuda_stereo_matching_backend.py:13-17). */
+int sd_compute_host(sd_handle *h, const void *left, const void *right, int dtype, int n_frames,
+                    float *out);
+
+/* Copies one intermediate of frame `frame` (index inside the last chunk) to device memory `dst`
+ * on `cuda_stream`. */
+int sd_get_stage(sd_handle *h, int stage, int frame, float *dst, void *cuda_stream);
+
+/* Debug/parity hook: when non-NULL, the fused kernel additionally stores the cost and aggregated
+ * volumes ([Hd,Wd,L] floats, d innermost, device memory) of frame 0 of each chunk -- the two
+ * tensors the reference materialises (buffer/device_buffer.cc:9-10).  Pass NULLs to switch off. */
+int sd_set_debug_volumes(sd_handle *h, float *cost_volume, float *aggregated_volume);
+
+/* Selects the fused-kernel variant: 0 = auto, 1 = generic (any radii), 2 = specialised
+ * (radii 1/4/10, cost radius 1).  SD_ERR_UNSUPPORTED if the configuration does not allow it. */
+int sd_set_variant(sd_handle *h, int variant);
+
+/* Number of kernels one sd_compute call launches for n_frames frames. */
+int sd_launches_per_call(sd_handle *h, int n_frames);
+
+int sd_frames_per_launch(sd_handle *h);
+const char *sd_last_error(sd_handle *h);
+int sd_last_cuda_error(sd_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STEREO_B200_H */

@@ -1,0 +1,136 @@
+"""ctypes binding of libstereo_b200.so (C ABI: include/stereo_b200.h).
+
+Fails loudly when the library is missing -- there is no fallback path.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libstereo_b200.so")
+
+SD_OK, SD_ERR_BAD_ARG, SD_ERR_SHAPE, SD_ERR_CUDA, SD_ERR_NOMEM, SD_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+SD_U8, SD_F32 = 0, 1
+STAGES = dict(gray_l=0, gray_r=1, pool_l=2, pool_r=3, wta=4, agg3=5, refined=6)
+
+CONFIG_FIELDS = ("height", "width", "downscale_factor", "min_disparity", "max_disparity",
+                 "ncc_patch_radius", "sad_patch_radius", "threshold",
+                 "small_mbm_radius", "mid_mbm_radius", "large_mbm_radius")
+
+# every symbol include/stereo_b200.h declares
+EXPORTS = ("sd_abi_version", "sd_config_default", "sd_dims", "sd_create", "sd_destroy", "sd_compute",
+           "sd_compute_host", "sd_get_stage", "sd_set_debug_volumes", "sd_set_variant",
+           "sd_launches_per_call", "sd_frames_per_launch", "sd_last_error", "sd_last_cuda_error")
+
+
+class SdConfig(C.Structure):
+    _fields_ = [(f, C.c_int32) for f in CONFIG_FIELDS]
+
+
+def build(force=False):
+    """Compile the library in-tree with nvcc (sm_100a).  Works without a GPU."""
+    import subprocess
+    cmd = ["make", "-C", os.path.join(HERE, "csrc"), "-j8"] + (["-B"] if force else [])
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  stereo_depth_b200 has no CPU/PyTorch fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, ip, fp = C.c_void_p, C.c_int, C.POINTER(C.c_float)
+    i32p = C.POINTER(C.c_int32)
+    L.sd_abi_version.restype = ip
+    L.sd_config_default.argtypes = [C.POINTER(SdConfig)]
+    L.sd_dims.argtypes = [C.POINTER(SdConfig), i32p, i32p, i32p]
+    L.sd_create.argtypes = [C.POINTER(SdConfig), ip, ip, C.POINTER(vp)]
+    L.sd_destroy.argtypes = [vp]
+    L.sd_compute.argtypes = [vp, vp, vp, ip, ip, vp, vp]
+    L.sd_compute_host.argtypes = [vp, vp, vp, ip, ip, vp]
+    L.sd_get_stage.argtypes = [vp, ip, ip, vp, vp]
+    L.sd_set_debug_volumes.argtypes = [vp, vp, vp]
+    L.sd_set_variant.argtypes = [vp, ip]
+    L.sd_launches_per_call.argtypes = [vp, ip]
+    L.sd_frames_per_launch.argtypes = [vp]
+    L.sd_last_error.argtypes = [vp]
+    L.sd_last_error.restype = C.c_char_p
+    L.sd_last_cuda_error.argtypes = [vp]
+    for n in EXPORTS:
+        getattr(L, n)  # AttributeError if the header and the library ever disagree
+    _lib = L
+    return L
+
+
+def default_config():
+    c = SdConfig()
+    lib().sd_config_default(C.byref(c))
+    return c
+
+
+def dims(cfg):
+    hd, wd, l = C.c_int32(), C.c_int32(), C.c_int32()
+    rc = lib().sd_dims(C.byref(cfg), C.byref(hd), C.byref(wd), C.byref(l))
+    if rc != SD_OK:
+        raise RuntimeError(f"invalid stereo matching configuration (sd_dims -> {rc})")
+    return hd.value, wd.value, l.value
+
+
+class Handle:
+    """Owns one sd_handle (device scratch for `frames_per_launch` frames)."""
+
+    def __init__(self, cfg, device, frames_per_launch=0):
+        self._h = C.c_void_p()
+        self.cfg = cfg
+        self.device = device
+        rc = lib().sd_create(C.byref(cfg), device, frames_per_launch, C.byref(self._h))
+        if rc != SD_OK:
+            msg = lib().sd_last_error(self._h).decode() if self._h else "allocation failed"
+            if self._h:
+                lib().sd_destroy(self._h)
+                self._h = C.c_void_p()
+            raise RuntimeError(f"sd_create failed ({rc}): {msg}")
+
+    def check(self, rc):
+        if rc != SD_OK:
+            raise RuntimeError(f"libstereo_b200 error {rc}: {lib().sd_last_error(self._h).decode()}")
+
+    def compute(self, left_ptr, right_ptr, dtype, n_frames, out_ptr, stream_ptr):
+        self.check(lib().sd_compute(self._h, left_ptr, right_ptr, dtype, n_frames, out_ptr, stream_ptr))
+
+    def compute_host(self, left_ptr, right_ptr, dtype, n_frames, out_ptr):
+        self.check(lib().sd_compute_host(self._h, left_ptr, right_ptr, dtype, n_frames, out_ptr))
+
+    def get_stage(self, stage, frame, dst_ptr, stream_ptr):
+        self.check(lib().sd_get_stage(self._h, STAGES[stage], frame, dst_ptr, stream_ptr))
+
+    def set_debug_volumes(self, cost_ptr, agg_ptr):
+        self.check(lib().sd_set_debug_volumes(self._h, cost_ptr, agg_ptr))
+
+    def set_variant(self, v):
+        self.check(lib().sd_set_variant(self._h, v))
+
+    def launches_per_call(self, n_frames):
+        return lib().sd_launches_per_call(self._h, n_frames)
+
+    @property
+    def frames_per_launch(self):
+        return lib().sd_frames_per_launch(self._h)
+
+    def close(self):
+        if self._h:
+            lib().sd_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,353 @@
+// C ABI of libstereo_b200.so (include/stereo_b200.h): handle, scratch, launch orchestration and
+// the pipelined host-buffer entry point.  Replaces the reference's host class
+// (src/csrc/depth/stereo_matching.cc:17-114) and its device_buffer (buffer/device_buffer.cc:3-12).
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+
+using namespace sd;
+
+namespace {
+constexpr int kSlots = 3;  // host pipeline depth (H2D / compute / D2H in flight)
+}
+
+struct sd_handle {
+    sd_config cfg;
+    Geom g;
+    int device;
+    int chunk;       // frames per launch
+    int variant;     // 0 auto, 1 generic, 2 fast
+    Scratch s;
+    float *dbg_cost, *dbg_agg;
+    // host pipeline (lazily created by sd_compute_host)
+    bool host_ready;
+    int host_dtype;
+    cudaStream_t st_h2d, st_comp, st_d2h;
+    void *din_l[kSlots], *din_r[kSlots];
+    float *dout[kSlots];
+    cudaEvent_t ev_h2d[kSlots], ev_comp[kSlots], ev_d2h[kSlots];
+    char err[320];
+    int last_cuda;
+};
+
+namespace {
+
+int fail(sd_handle *h, int code, const char *msg) {
+    if (h) snprintf(h->err, sizeof(h->err), "%s", msg);
+    return code;
+}
+
+int fail_cuda(sd_handle *h, cudaError_t e, const char *where) {
+    if (h) {
+        h->last_cuda = (int)e;
+        snprintf(h->err, sizeof(h->err), "CUDA error at %s: %s (%d)", where, cudaGetErrorString(e), (int)e);
+    }
+    return SD_ERR_CUDA;
+}
+
+#define SD_CUDA(h, call)                                        \
+    do {                                                        \
+        cudaError_t e__ = (call);                               \
+        if (e__ != cudaSuccess) return fail_cuda(h, e__, #call); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev;
+    bool ok;
+    explicit DeviceGuard(int dev) : prev(-1), ok(false) {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        ok = (prev == dev) || (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+const char *validate(const sd_config *c) {
+    if (c->height <= 0 || c->width <= 0) return "height and width must be positive";
+    if (c->downscale_factor <= 0) return "downscale_factor must be positive";
+    if (c->min_disparity < 0) return "min_disparity must be >= 0";
+    if (c->max_disparity < c->min_disparity) return "max_disparity must be >= min_disparity";
+    if (c->ncc_patch_radius < 0 || c->sad_patch_radius < 0) return "patch radii must be >= 0";
+    if (c->small_mbm_radius < 0 || c->mid_mbm_radius < 0 || c->large_mbm_radius < 0) return "mbm radii must be >= 0";
+    if (c->small_mbm_radius > c->large_mbm_radius || c->mid_mbm_radius > c->large_mbm_radius)
+        return "small/mid mbm radius must not exceed large_mbm_radius (the reference's tile only covers the large radius)";
+    if (c->threshold < 0) return "threshold must be >= 0";
+    return nullptr;
+}
+
+size_t in_bytes_per_frame(const sd_handle *h, int dtype) {
+    return (size_t)3 * h->g.H * h->g.W * (dtype == SD_U8 ? 1 : 4);
+}
+
+__global__ void extract_wta(const float4 *__restrict__ w, float *__restrict__ dst, int n, float min_ds) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __fadd_rn(w[i].x, min_ds);
+}
+
+__global__ void extract_agg3(const float4 *__restrict__ w, const float2 *__restrict__ e, float *__restrict__ dst, int n,
+                             int L) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 v = w[i];
+    const float2 ed = e[i];
+    const int bd = (int)v.x;
+    dst[3 * i + 0] = (bd == 0) ? ed.y : v.y;
+    dst[3 * i + 1] = (bd == 0) ? ed.x : v.z;
+    dst[3 * i + 2] = (bd == L - 1) ? ed.x : v.w;
+}
+
+int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int frames, float *out, cudaStream_t st) {
+    SD_CUDA(h, launch_gray_pool(h->g, left, right, dtype, frames, h->s, st));
+    const bool fast = (h->variant == 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g));
+    if (fast) SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
+    else SD_CUDA(h, launch_mbm_wta_generic(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
+    SD_CUDA(h, launch_secondary(h->g, frames, h->s, st));
+    SD_CUDA(h, launch_fill(h->g, frames, h->s, out, st));
+    return SD_OK;
+}
+
+void destroy_host_pipeline(sd_handle *h) {
+    if (!h->host_ready) return;
+    for (int i = 0; i < kSlots; i++) {
+        cudaFree(h->din_l[i]);
+        cudaFree(h->din_r[i]);
+        cudaFree(h->dout[i]);
+        cudaEventDestroy(h->ev_h2d[i]);
+        cudaEventDestroy(h->ev_comp[i]);
+        cudaEventDestroy(h->ev_d2h[i]);
+    }
+    cudaStreamDestroy(h->st_h2d);
+    cudaStreamDestroy(h->st_comp);
+    cudaStreamDestroy(h->st_d2h);
+    h->host_ready = false;
+}
+
+int ensure_host_pipeline(sd_handle *h, int dtype) {
+    if (h->host_ready && h->host_dtype == dtype) return SD_OK;
+    destroy_host_pipeline(h);
+    const size_t inb = in_bytes_per_frame(h, dtype) * h->chunk;
+    const size_t outb = (size_t)h->g.H * h->g.W * sizeof(float) * h->chunk;
+    memset(h->din_l, 0, sizeof(h->din_l));
+    memset(h->din_r, 0, sizeof(h->din_r));
+    memset(h->dout, 0, sizeof(h->dout));
+    SD_CUDA(h, cudaStreamCreateWithFlags(&h->st_h2d, cudaStreamNonBlocking));
+    SD_CUDA(h, cudaStreamCreateWithFlags(&h->st_comp, cudaStreamNonBlocking));
+    SD_CUDA(h, cudaStreamCreateWithFlags(&h->st_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < kSlots; i++) {
+        SD_CUDA(h, cudaMalloc(&h->din_l[i], inb));
+        SD_CUDA(h, cudaMalloc(&h->din_r[i], inb));
+        SD_CUDA(h, cudaMalloc((void **)&h->dout[i], outb));
+        SD_CUDA(h, cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+        SD_CUDA(h, cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+        SD_CUDA(h, cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming));
+    }
+    h->host_ready = true;
+    h->host_dtype = dtype;
+    return SD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sd_abi_version(void) { return SD_ABI_VERSION; }
+
+int sd_config_default(sd_config *cfg) {
+    if (!cfg) return SD_ERR_BAD_ARG;
+    const sd_config d = {1080, 1920, 2, 75, 262, 1, 5, 5, 1, 4, 10};
+    *cfg = d;
+    return SD_OK;
+}
+
+int sd_dims(const sd_config *c, int32_t *Hd, int32_t *Wd, int32_t *L) {
+    if (!c || validate(c)) return SD_ERR_BAD_ARG;
+    const int K = c->downscale_factor;
+    if (Hd) *Hd = (c->height + K - 1) / K;
+    if (Wd) *Wd = (c->width + K - 1) / K;
+    if (L) *L = c->max_disparity / K - c->min_disparity / K + 1;
+    return SD_OK;
+}
+
+int sd_create(const sd_config *cfg, int device, int frames_per_launch, sd_handle **out) {
+    if (!cfg || !out) return SD_ERR_BAD_ARG;
+    *out = nullptr;
+    sd_handle *h = new (std::nothrow) sd_handle();
+    if (!h) return SD_ERR_NOMEM;
+    memset(h, 0, sizeof(*h));
+    *out = h;  // returned even on failure so the caller can read sd_last_error, then sd_destroy
+    h->cfg = *cfg;
+    h->device = device;
+    if (const char *why = validate(cfg)) return fail(h, SD_ERR_BAD_ARG, why);
+    Geom &g = h->g;
+    g.H = cfg->height;
+    g.W = cfg->width;
+    g.K = cfg->downscale_factor;
+    sd_dims(cfg, &g.Hd, &g.Wd, &g.L);
+    g.min_ds = cfg->min_disparity / g.K;
+    g.r_cost = cfg->ncc_patch_radius;
+    g.r_sad = cfg->sad_patch_radius;
+    g.rs = cfg->small_mbm_radius;
+    g.rm = cfg->mid_mbm_radius;
+    g.rl = cfg->large_mbm_radius;
+    g.threshold = (float)cfg->threshold;
+    if (frames_per_launch <= 0) {
+        // default: keep one chunk's working set (gray+pooled+outputs) well inside the 126 MB L2
+        const size_t per_frame = (size_t)g.H * g.W * 4 * 3 + (size_t)g.Hd * g.Wd * 36;
+        frames_per_launch = (int)((48u << 20) / (per_frame ? per_frame : 1));
+        if (frames_per_launch < 1) frames_per_launch = 1;
+        if (frames_per_launch > 8) frames_per_launch = 8;
+    }
+    h->chunk = frames_per_launch;
+
+    int ndev = 0;
+    SD_CUDA(h, cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(h, SD_ERR_BAD_ARG, "no such CUDA device");
+    DeviceGuard dg(device);
+    if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
+    const size_t F = h->chunk, n = (size_t)g.H * g.W, nd = (size_t)g.Hd * g.Wd;
+    SD_CUDA(h, cudaMalloc((void **)&h->s.gray, F * 2 * n * sizeof(float)));
+    SD_CUDA(h, cudaMalloc((void **)&h->s.pool, F * 2 * nd * sizeof(float)));
+    SD_CUDA(h, cudaMalloc((void **)&h->s.wta4, F * nd * sizeof(float4)));
+    SD_CUDA(h, cudaMalloc((void **)&h->s.edge2, F * nd * sizeof(float2)));
+    SD_CUDA(h, cudaMalloc((void **)&h->s.refined, F * nd * sizeof(float)));
+    return SD_OK;
+}
+
+int sd_destroy(sd_handle *h) {
+    if (!h) return SD_OK;
+    {
+        DeviceGuard dg(h->device);
+        destroy_host_pipeline(h);
+        cudaFree(h->s.gray);
+        cudaFree(h->s.pool);
+        cudaFree(h->s.wta4);
+        cudaFree(h->s.edge2);
+        cudaFree(h->s.refined);
+    }
+    delete h;
+    return SD_OK;
+}
+
+int sd_compute(sd_handle *h, const void *left, const void *right, int dtype, int n_frames, float *out, void *stream) {
+    if (!h) return SD_ERR_BAD_ARG;
+    if (!left || !right || !out) return fail(h, SD_ERR_BAD_ARG, "null image pointer");
+    if (dtype != SD_U8 && dtype != SD_F32) return fail(h, SD_ERR_SHAPE, "dtype must be SD_U8 or SD_F32");
+    if (n_frames <= 0) return fail(h, SD_ERR_SHAPE, "n_frames must be positive");
+    DeviceGuard dg(h->device);
+    if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t inb = in_bytes_per_frame(h, dtype), outn = (size_t)h->g.H * h->g.W;
+    for (int f0 = 0; f0 < n_frames; f0 += h->chunk) {
+        const int nf = (n_frames - f0 < h->chunk) ? n_frames - f0 : h->chunk;
+        const int rc = run_chunk(h, (const char *)left + inb * f0, (const char *)right + inb * f0, dtype, nf,
+                                 out + outn * f0, st);
+        if (rc != SD_OK) return rc;
+    }
+    return SD_OK;
+}
+
+int sd_compute_host(sd_handle *h, const void *left, const void *right, int dtype, int n_frames, float *out) {
+    if (!h) return SD_ERR_BAD_ARG;
+    if (!left || !right || !out) return fail(h, SD_ERR_BAD_ARG, "null image pointer");
+    if (dtype != SD_U8 && dtype != SD_F32) return fail(h, SD_ERR_SHAPE, "dtype must be SD_U8 or SD_F32");
+    if (n_frames <= 0) return fail(h, SD_ERR_SHAPE, "n_frames must be positive");
+    DeviceGuard dg(h->device);
+    if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
+    int rc = ensure_host_pipeline(h, dtype);
+    if (rc != SD_OK) return rc;
+    const size_t inb = in_bytes_per_frame(h, dtype), outn = (size_t)h->g.H * h->g.W;
+    int it = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += h->chunk, it++) {
+        const int nf = (n_frames - f0 < h->chunk) ? n_frames - f0 : h->chunk;
+        const int sl = it % kSlots;
+        // inputs of slot sl may be overwritten once the kernels of its previous use are done
+        if (it >= kSlots) SD_CUDA(h, cudaStreamWaitEvent(h->st_h2d, h->ev_comp[sl], 0));
+        SD_CUDA(h, cudaMemcpyAsync(h->din_l[sl], (const char *)left + inb * f0, inb * nf, cudaMemcpyHostToDevice, h->st_h2d));
+        SD_CUDA(h, cudaMemcpyAsync(h->din_r[sl], (const char *)right + inb * f0, inb * nf, cudaMemcpyHostToDevice, h->st_h2d));
+        SD_CUDA(h, cudaEventRecord(h->ev_h2d[sl], h->st_h2d));
+        SD_CUDA(h, cudaStreamWaitEvent(h->st_comp, h->ev_h2d[sl], 0));
+        // the output of slot sl may be overwritten once its previous D2H is done
+        if (it >= kSlots) SD_CUDA(h, cudaStreamWaitEvent(h->st_comp, h->ev_d2h[sl], 0));
+        rc = run_chunk(h, h->din_l[sl], h->din_r[sl], dtype, nf, h->dout[sl], h->st_comp);
+        if (rc != SD_OK) return rc;
+        SD_CUDA(h, cudaEventRecord(h->ev_comp[sl], h->st_comp));
+        SD_CUDA(h, cudaStreamWaitEvent(h->st_d2h, h->ev_comp[sl], 0));
+        SD_CUDA(h, cudaMemcpyAsync(out + outn * f0, h->dout[sl], outn * nf * sizeof(float), cudaMemcpyDeviceToHost, h->st_d2h));
+        SD_CUDA(h, cudaEventRecord(h->ev_d2h[sl], h->st_d2h));
+    }
+    SD_CUDA(h, cudaStreamSynchronize(h->st_d2h));
+    SD_CUDA(h, cudaStreamSynchronize(h->st_comp));
+    return SD_OK;
+}
+
+int sd_get_stage(sd_handle *h, int stage, int frame, float *dst, void *stream) {
+    if (!h) return SD_ERR_BAD_ARG;
+    if (!dst) return fail(h, SD_ERR_BAD_ARG, "null destination");
+    if (frame < 0 || frame >= h->chunk) return fail(h, SD_ERR_SHAPE, "frame index outside the chunk");
+    DeviceGuard dg(h->device);
+    if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Geom &g = h->g;
+    const size_t n = (size_t)g.H * g.W, nd = (size_t)g.Hd * g.Wd;
+    const int threads = 256, blocks = (int)((nd + threads - 1) / threads);
+    switch (stage) {
+        case SD_STAGE_GRAY_L:
+        case SD_STAGE_GRAY_R:
+            SD_CUDA(h, cudaMemcpyAsync(dst, h->s.gray + ((size_t)frame * 2 + (stage - SD_STAGE_GRAY_L)) * n, n * 4,
+                                       cudaMemcpyDeviceToDevice, st));
+            break;
+        case SD_STAGE_POOL_L:
+        case SD_STAGE_POOL_R:
+            SD_CUDA(h, cudaMemcpyAsync(dst, h->s.pool + ((size_t)frame * 2 + (stage - SD_STAGE_POOL_L)) * nd, nd * 4,
+                                       cudaMemcpyDeviceToDevice, st));
+            break;
+        case SD_STAGE_WTA:
+            extract_wta<<<blocks, threads, 0, st>>>(h->s.wta4 + frame * nd, dst, (int)nd, (float)g.min_ds);
+            SD_CUDA(h, cudaGetLastError());
+            break;
+        case SD_STAGE_AGG3:
+            extract_agg3<<<blocks, threads, 0, st>>>(h->s.wta4 + frame * nd, h->s.edge2 + frame * nd, dst, (int)nd, g.L);
+            SD_CUDA(h, cudaGetLastError());
+            break;
+        case SD_STAGE_REFINED:
+            SD_CUDA(h, cudaMemcpyAsync(dst, h->s.refined + frame * nd, nd * 4, cudaMemcpyDeviceToDevice, st));
+            break;
+        default:
+            return fail(h, SD_ERR_SHAPE, "unknown stage");
+    }
+    return SD_OK;
+}
+
+int sd_set_debug_volumes(sd_handle *h, float *cost_volume, float *aggregated_volume) {
+    if (!h) return SD_ERR_BAD_ARG;
+    h->dbg_cost = cost_volume;
+    h->dbg_agg = aggregated_volume;
+    return SD_OK;
+}
+
+int sd_set_variant(sd_handle *h, int variant) {
+    if (!h) return SD_ERR_BAD_ARG;
+    if (variant < 0 || variant > 2) return fail(h, SD_ERR_BAD_ARG, "variant must be 0, 1 or 2");
+    if (variant == 2 && !mbm_wta_fast_supported(h->g))
+        return fail(h, SD_ERR_UNSUPPORTED, "specialised fused kernel needs radii 1/4/10, cost radius 1");
+    h->variant = variant;
+    return SD_OK;
+}
+
+int sd_launches_per_call(sd_handle *h, int n_frames) {
+    if (!h || n_frames <= 0) return 0;
+    return 4 * ((n_frames + h->chunk - 1) / h->chunk);
+}
+
+int sd_frames_per_launch(sd_handle *h) { return h ? h->chunk : 0; }
+
+const char *sd_last_error(sd_handle *h) { return h ? h->err : "null handle"; }
+
+int sd_last_cuda_error(sd_handle *h) { return h ? h->last_cuda : 0; }
+
+}  // extern "C"

@@ -1,0 +1,59 @@
+// Shared declarations of libstereo_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/stereo_b200.h"
+
+namespace sd {
+
+// std::numeric_limits<float>::min() -- the reference's WTA / secondary-matching initial "best"
+// (wta_disparity_selection.cu:22, secondary_matching.cu:45).
+constexpr float kFltMin = 1.17549435e-38f;
+
+// True modulo: the SAFE definition of the reference's pad_index (device_functions.cuh:10-20).
+// Identical to pad_index wherever pad_index stays inside the tensor (index in [-n, n]); for
+// index > n, where the reference forms a negative flat offset, we wrap instead.
+__host__ __device__ __forceinline__ int wrapm(int i, int n) {
+    if ((unsigned)i < (unsigned)n) return i;
+    i %= n;
+    return i < 0 ? i + n : i;
+}
+
+// Geometry shared by all kernels of one handle.
+struct Geom {
+    int H, W, K, Hd, Wd, L;
+    int min_ds;        // min_disparity / K   (stereo_matching.cc:61)
+    int r_cost;        // ncc_patch_radius
+    int r_sad;         // sad_patch_radius
+    int rs, rm, rl;    // small / mid / large multi-block radii
+    float threshold;
+};
+
+// Per-chunk scratch in HBM (frame-major; one chunk = frames_per_launch frames).
+//   gray  : [F][2][H][W]    float   (side 0 = left, 1 = right)
+//   pool  : [F][2][Hd][Wd]  float
+//   wta4  : [F][Hd][Wd]     float4  (d* relative as float, A[d*-1], max A, A[d*+1]) -- raw, see secondary.cu
+//   edge2 : [F][Hd][Wd]     float2  (A[0], A[L-1])  for the circular wrap of d*-1 / d*+1
+//   refined:[F][Hd][Wd]     float
+struct Scratch {
+    float *gray;
+    float *pool;
+    float4 *wta4;
+    float2 *edge2;
+    float *refined;
+};
+
+// kernel launchers (each returns cudaGetLastError())
+cudaError_t launch_gray_pool(const Geom &g, const void *left, const void *right, int dtype, int frames,
+                             const Scratch &s, cudaStream_t st);
+cudaError_t launch_mbm_wta_generic(const Geom &g, int frames, const Scratch &s, float *dbg_cost,
+                                   float *dbg_agg, cudaStream_t st);
+bool mbm_wta_fast_supported(const Geom &g);
+cudaError_t launch_mbm_wta_fast(const Geom &g, int frames, const Scratch &s, float *dbg_cost,
+                                float *dbg_agg, cudaStream_t st);
+cudaError_t launch_secondary(const Geom &g, int frames, const Scratch &s, cudaStream_t st);
+cudaError_t launch_fill(const Geom &g, int frames, const Scratch &s, float *out, cudaStream_t st);
+
+}  // namespace sd

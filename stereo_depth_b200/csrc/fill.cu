@@ -1,0 +1,100 @@
+// Kernel D+E: disparity upscale + vertical bilateral fill + horizontal bilateral fill, fused.
+//
+// Reference: upscale_disparity_vertical_fill.cu:20-51 then horizontal_disparity_fill.cu:19-40
+// (two kernels, the second in place).  The horizontal pass only ever reads columns that are
+// multiples of K, and those hold exactly what the vertical pass wrote, so every output pixel is a
+// pure function of the refined disparity and the left gray image:
+//   vf(r, c)  for c % K == 0:  x = r / K, i = r % K, p = K*disp[x][c/K]
+//        i == 0            -> p
+//        n = K*disp[x-1][c/K];  |p-n| <= thr -> p + (i*(n-p))/K
+//        else  cur=GL[r][c]:  |cur-GL[Kx][c]| <= |cur-GL[(K+1)x][c]| ? p : n      (sic: (K+1)*x)
+//   out(r, c): m = c % K, nk = c - m, p = vf(r,nk), n = vf(r,nk+K)
+//        |p-n| <= thr -> p + (m*(n-p))/K   else colour pick between GL[r][nk], GL[r][nk+K]
+// SAFE definitions where the reference is undefined (oracle/stereo_oracle.c so_vfill/so_hfill):
+//   rows 1..K-1 of the image (never written by the reference) replicate p;
+//   GL[(K+1)x] wraps modulo H;  column nk+K == W reads the next row's column 0 like the
+//   reference's flat index does, and p on the last row / when W % K != 0.
+// HBM-bound: reads disp [Hd,Wd] and (rarely) gray, writes [H,W]; 4 pixels per thread, STG.128.
+#include "common.cuh"
+
+namespace sd {
+namespace {
+
+__device__ __forceinline__ float vfill_value(const Geom &g, const float *__restrict__ gl,
+                                             const float *__restrict__ disp, int r, int c) {
+    const int K = g.K, x = r / K, i = r - x * K, yd = c / K;
+    const float fk = (float)K;
+    const float p = __fmul_rn(fk, __ldg(disp + (size_t)x * g.Wd + yd));
+    if (i == 0 || x == 0) return p;
+    const float n = __fmul_rn(fk, __ldg(disp + (size_t)(x - 1) * g.Wd + yd));
+    if (fabsf(__fsub_rn(p, n)) <= g.threshold)
+        return __fadd_rn(p, __fdiv_rn(__fmul_rn((float)i, __fsub_rn(n, p)), fk));
+    const float prev_color = __ldg(gl + (size_t)(K * x) * g.W + c);
+    const float next_color = __ldg(gl + (size_t)wrapm((K + 1) * x, g.H) * g.W + c);
+    const float cur = __ldg(gl + (size_t)r * g.W + c);
+    return (fabsf(__fsub_rn(cur, prev_color)) <= fabsf(__fsub_rn(cur, next_color))) ? p : n;
+}
+
+__device__ __forceinline__ float hfill_value(const Geom &g, const float *__restrict__ gl, int r, int c, int nk,
+                                             float p, float n) {
+    const int m = c - nk;
+    if (fabsf(__fsub_rn(p, n)) <= g.threshold)
+        return __fadd_rn(p, __fdiv_rn(__fmul_rn((float)m, __fsub_rn(n, p)), (float)g.K));
+    const size_t o = (size_t)r * g.W;
+    const float pc = __ldg(gl + o + nk);
+    const size_t cf = o + nk + g.K;
+    const float nc = (cf < (size_t)g.H * g.W) ? __ldg(gl + cf) : pc;
+    const float cur = __ldg(gl + o + c);
+    return (fabsf(__fsub_rn(cur, pc)) <= fabsf(__fsub_rn(cur, nc))) ? p : n;
+}
+
+// value of the "next" mod-K sample to the right of nk on row r
+__device__ __forceinline__ float next_sample(const Geom &g, const float *__restrict__ gl,
+                                             const float *__restrict__ disp, int r, int nk, float p) {
+    if (nk + g.K < g.W) return vfill_value(g, gl, disp, r, nk + g.K);
+    if (g.W % g.K == 0 && r + 1 < g.H) return vfill_value(g, gl, disp, r + 1, 0);
+    return p;
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(Geom g, const float *__restrict__ gray,
+                                                   const float *__restrict__ refined, float *__restrict__ out, bool vec_ok) {
+    const int c4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int r = blockIdx.y * blockDim.y + threadIdx.y;
+    const int frame = blockIdx.z;
+    if (r >= g.H || c4 >= g.W) return;
+    const size_t plane = (size_t)g.H * g.W;
+    const float *gl = gray + (size_t)frame * 2 * plane;
+    const float *disp = refined + (size_t)frame * g.Hd * g.Wd;
+    float *o = out + (size_t)frame * plane + (size_t)r * g.W + c4;
+    float v[4];
+    int nk_cached = -1;
+    float p = 0.0f, n = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int c = c4 + k;
+        if (c >= g.W) break;
+        const int nk = c - c % g.K;
+        if (nk != nk_cached) {
+            p = (nk_cached >= 0 && nk == nk_cached + g.K) ? n : vfill_value(g, gl, disp, r, nk);
+            n = next_sample(g, gl, disp, r, nk, p);
+            nk_cached = nk;
+        }
+        v[k] = hfill_value(g, gl, r, c, nk, p, n);
+    }
+    if (vec_ok && c4 + 3 < g.W) {
+        *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+        for (int k = 0; k < 4 && c4 + k < g.W; k++) o[k] = v[k];
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_fill(const Geom &g, int frames, const Scratch &s, float *out, cudaStream_t st) {
+    dim3 block(32, 8), grid(((g.W + 3) / 4 + 31) / 32, (g.H + 7) / 8, frames);
+    const bool vec_ok = (g.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+    fill_kernel<<<grid, block, 0, st>>>(g, s.gray, s.refined, out, vec_ok);
+    return cudaGetLastError();
+}
+
+}  // namespace sd

@@ -1,0 +1,152 @@
+// Kernel C: secondary matching on the full-resolution gray images + the two parabola fits.
+//
+// Reference: secondary_matching.cu:24-71 with device_functions.cuh:22-73.  Per downscaled pixel:
+//   dm   = int(d_wta);  candidates s in [K(dm-1), K(dm+1)];
+//   S(s) = chain from 0.0f over i,j in [-r,r] (rows outer) of 255 - |GL[xK+i][yK+j] - GR[xK+i][yK+j-s]|
+//   ds   = first arg-max of S (strict >, init FLT_MIN, default K(dm-1));
+//   only if K(dm-1) < ds < K(dm+1):
+//     qm = peak(dm, A[dm], dm+1, A[dm+1], dm-1, A[dm-1])   (A = aggregated cost, circular in d)
+//     qs = peak(ds, S(ds), ds+1, S(ds+1), ds-1, S(ds-1))   (both neighbours are candidates already)
+//     dm' = qm - dm; ds' = qs - ds; t = (ds + ds') - K dm
+//     out = dm' * t > 0 ? (ds + ds')/K : ((dm + dm') + (ds + ds')/K) / 2
+// The parabola's FMA contraction pattern follows the reference's SASS (see oracle/stereo_oracle.c).
+// The aggregated volume is never in HBM: kernel B left (d*, A[d*-1], max A, A[d*+1]) and (A[0], A[L-1]).
+// With min_disparity != 0 the reference indexes the volume with the absolute disparity
+// (secondary_matching.cu:28-31, a bug); we use the relative index (documented deviation).
+#include "common.cuh"
+
+namespace sd {
+namespace {
+
+__device__ __forceinline__ float quad_peak(float x1, float y1, float x2, float y2, float x3, float y3) {
+    const float den = __fmul_rn(__fmul_rn(__fsub_rn(x1, x2), __fsub_rn(x2, x3)), __fsub_rn(x1, x3));
+    float m;
+    if (y1 > y2) m = (y1 > y3) ? x1 : x3;
+    else m = (y2 > y3) ? x2 : x3;
+    if (den != 0.0f) {
+        const float a = __fmaf_rn(x1, __fsub_rn(y3, y2), __fmaf_rn(x3, __fsub_rn(y2, y1), __fmul_rn(x2, __fsub_rn(y1, y3))));
+        const float b = __fmaf_rn(__fmul_rn(x2, x2), __fsub_rn(y3, y1),
+                                  __fmaf_rn(__fmul_rn(x3, x3), __fsub_rn(y1, y2),
+                                            __fmul_rn(__fmul_rn(x1, x1), __fsub_rn(y2, y3))));
+        if (a < 0.0f) m = __fdiv_rn(-b, __fadd_rn(a, a));
+    }
+    return m;
+}
+
+// NC = number of candidates kept in registers (2K+1); NC == 0: runtime K, neighbours recomputed.
+template <int KT>
+__global__ void __launch_bounds__(128) secondary_kernel(Geom g, const float *__restrict__ gray,
+                                                        const float4 *__restrict__ wta4,
+                                                        const float2 *__restrict__ edge2, float *__restrict__ refined) {
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x = blockIdx.y * blockDim.y + threadIdx.y;
+    const int frame = blockIdx.z;
+    if (x >= g.Hd || y >= g.Wd) return;
+    const int K = KT > 0 ? KT : g.K;
+    const int H = g.H, W = g.W, r = g.r_sad;
+    const size_t plane = (size_t)H * W;
+    const float *gl = gray + (size_t)frame * 2 * plane, *gr = gl + plane;
+    const size_t o = (size_t)frame * g.Hd * g.Wd + (size_t)x * g.Wd + y;
+    const float4 w = wta4[o];
+    const int bd = (int)w.x;
+    const float dispf = __fadd_rn(w.x, (float)g.min_ds);  // wta_disparity_selection.cu:30
+    const int dm = (int)dispf;
+    const int lo = K * (dm - 1), hi = K * (dm + 1);
+    float result = dispf;
+
+    constexpr int NC = KT > 0 ? 2 * KT + 1 : 1;
+    float S[NC];
+    float c_sad = kFltMin;
+    int d_sad = lo;
+    if (KT > 0) {
+#pragma unroll
+        for (int k = 0; k < NC; k++) S[k] = 0.0f;
+        for (int i = -r; i <= r; i++) {
+            const size_t ro = (size_t)wrapm(x * K + i, H) * W;
+            for (int j = -r; j <= r; j++) {
+                const int c = y * K + j;
+                const float l = __ldg(gl + ro + wrapm(c, W));
+#pragma unroll
+                for (int k = 0; k < NC; k++) {
+                    const float rr = __ldg(gr + ro + wrapm(c - (lo + k), W));
+                    S[k] = __fadd_rn(S[k], __fsub_rn(255.0f, fabsf(__fsub_rn(l, rr))));
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NC; k++)
+            if (S[k] > c_sad) {
+                c_sad = S[k];
+                d_sad = lo + k;
+            }
+    } else {
+        for (int s = lo; s <= hi; s++) {
+            float c = 0.0f;
+            for (int i = -r; i <= r; i++) {
+                const size_t ro = (size_t)wrapm(x * K + i, H) * W;
+                for (int j = -r; j <= r; j++) {
+                    const float l = __ldg(gl + ro + wrapm(y * K + j, W));
+                    const float rr = __ldg(gr + ro + wrapm(y * K + j - s, W));
+                    c = __fadd_rn(c, __fsub_rn(255.0f, fabsf(__fsub_rn(l, rr))));
+                }
+            }
+            if (c > c_sad) {
+                c_sad = c;
+                d_sad = s;
+            }
+        }
+    }
+
+    if (d_sad > lo && d_sad < hi) {
+        float sp = 0.0f, sm = 0.0f;
+        if (KT > 0) {
+#pragma unroll
+            for (int k = 1; k < NC - 1; k++)
+                if (lo + k == d_sad) {
+                    sp = S[k + 1];
+                    sm = S[k - 1];
+                }
+        } else {
+            for (int i = -r; i <= r; i++) {
+                const size_t ro = (size_t)wrapm(x * K + i, H) * W;
+                for (int j = -r; j <= r; j++) {
+                    const float l = __ldg(gl + ro + wrapm(y * K + j, W));
+                    const float rp = __ldg(gr + ro + wrapm(y * K + j - (d_sad + 1), W));
+                    const float rm = __ldg(gr + ro + wrapm(y * K + j - (d_sad - 1), W));
+                    sp = __fadd_rn(sp, __fsub_rn(255.0f, fabsf(__fsub_rn(l, rp))));
+                    sm = __fadd_rn(sm, __fsub_rn(255.0f, fabsf(__fsub_rn(l, rm))));
+                }
+            }
+        }
+        const float2 e = edge2[o];
+        const float a_d = (bd == 0) ? e.x : w.z;
+        const float a_m1 = (bd == 0) ? e.y : w.y;
+        const float a_p1 = (bd == g.L - 1) ? e.x : w.w;
+        const float fdm = (float)dm, fds = (float)d_sad, fk = (float)K;
+        const float qm = quad_peak(fdm, a_d, (float)(dm + 1), a_p1, (float)(dm - 1), a_m1);
+        const float qs = quad_peak(fds, c_sad, (float)(d_sad + 1), sp, (float)(d_sad - 1), sm);
+        const float delta_mbm = __fsub_rn(qm, fdm);
+        const float delta_sad = __fsub_rn(qs, fds);
+        const float pos = __fadd_rn(fds, delta_sad);
+        const float t = __fsub_rn(pos, (float)(K * dm));
+        if (__fmul_rn(delta_mbm, t) > 0.0f) result = __fdiv_rn(pos, fk);
+        else result = __fmul_rn(__fadd_rn(__fadd_rn(fdm, delta_mbm), __fdiv_rn(pos, fk)), 0.5f);
+    }
+    refined[o] = result;
+}
+
+}  // namespace
+
+cudaError_t launch_secondary(const Geom &g, int frames, const Scratch &s, cudaStream_t st) {
+    dim3 block(32, 4), grid((g.Wd + 31) / 32, (g.Hd + 3) / 4, frames);
+    switch (g.K) {
+        case 1: secondary_kernel<1><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.refined); break;
+        case 2: secondary_kernel<2><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.refined); break;
+        case 3: secondary_kernel<3><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.refined); break;
+        case 4: secondary_kernel<4><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.refined); break;
+        default: secondary_kernel<0><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.refined); break;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace sd
