@@ -115,7 +115,7 @@ def test_quadratic_peak_cases():
     assert O.quad_peak(5, 10.0, 6, 4.0, 4, 7.0) == 5.0
     # ties: y1 > y2 false -> x2 or x3
     assert O.quad_peak(5, 1.0, 6, 1.0, 4, 1.0) == 4.0
-    assert O.quad_peak(5, 1.0, 6, 2.0, 4, 1.0) == 6.0
+    assert O.quad_peak(5, 1.0, 6, 2.0, 4, 0.0) == 6.0   # a == 0: fallback branch picks x2
     # a < 0 (centre is a minimum): -b / 2a
     x1, y1, x2, y2, x3, y3 = 5.0, 1.0, 6.0, 4.0, 4.0, 3.0
     a = x3 * (y2 - y1) + x2 * (y1 - y3) + x1 * (y3 - y2)
