@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""Benchmark of the stereo-matching hot path (BASELINE.json metric: frames/s at 1920x1080, D=128, K=2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the whole hot path (gray+pool, fused cost+aggregation+WTA, secondary matching,
+upscale+fill) over a batch of `--frames` synthetic random-dot frames per GPU.  Frames are sharded over
+GPUs (one process per GPU, no collective on the data path) => weak scaling.  Prints ONE JSON line.
+
+  value      frames/s, inputs (uint8 CHW, what a camera delivers) already resident in HBM, CUDA events
+  e2e        frames/s through CudaStereoMatchingBackend.process_batch with pinned HOST tensors: every step
+             copies its inputs host->device and its disparity maps device->host (pipelined by the library)
+  roofline   dominant kernel (fused cost+aggregation+WTA): algorithmic fp32 lane-ops / measured launch time
+             vs the measured fp32-add peak of the CUDA cores (not HBM, not tensor cores: SURVEY 8-d)
+  cpu_baseline  the CPU oracle (order-faithful port of the reference kernels) on this box's host cores
+  reference_cuda  the reference's own CUDA kernels (oracle/_ref build) on the same B200, same run
+
+--impl reference times the reference itself: its CUDA kernels when oracle/_ref/cuda_depth.so loads (the
+reference has no CPU implementation), else the oracle port on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: the configuration the metric is quoted on
+    "C3": dict(H=1080, W=1920, K=2, D=128, name="1920x1080 synthetic random-dot video, D=128, K=2"),
+    "C5": dict(H=720, W=1280, K=2, D=128, name="1280x720 synthetic random-dot video, D=128, K=2"),
+    "C1": dict(H=480, W=640, K=2, D=64, name="640x480 synthetic random-dot pair, D=64, K=2"),
+}
+FADD_PEAK_TOPS = 37.0  # measured on this pool's B200: tools/microbench/fadd_bench (profiles/r01_fadd_microbench.txt)
+SMI_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--frames", type=int, default=64, help="frames per step per GPU")
+    p.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    p.add_argument("--frames-per-launch", type=int, default=8)
+    p.add_argument("--distinct", type=int, default=8, help="distinct synthetic frames generated (tiled to --frames)")
+    p.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / reference_cuda legs")
+    return p.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, f"/tmp/bench_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={SMI_QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load": samples drawing clearly more than idle power
+        load = [c for c, p in zip(sm, power) if p >= 0.6 * max(power)] or sm
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+def dist_setup(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+    return rank, world, local
+
+
+def barrier(world):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world):
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def make_inputs(wl, frames, distinct, rank):
+    import numpy as np
+    import torch
+    from stereo_depth_b200.synthetic import make_batch
+    distinct = max(1, min(distinct, frames))
+    l, r = make_batch(distinct, wl["H"], wl["W"], wl["D"], seed=1234, first_frame=rank * frames)
+    reps = (frames + distinct - 1) // distinct
+    l = np.concatenate([l] * reps)[:frames]
+    r = np.concatenate([r] * reps)[:frames]
+    return torch.from_numpy(l), torch.from_numpy(r)
+
+
+def cpu_baseline_leg(wl):
+    """Bounded sample: one frame of the workload through the oracle on the host cores."""
+    import numpy as np
+    from oracle import oracle as O
+    from stereo_depth_b200.synthetic import make_pair
+    l, r, _ = make_pair(wl["H"], wl["W"], wl["D"], seed=1234)
+    cfg = O.make_config(height=wl["H"], width=wl["W"], downscale_factor=wl["K"], min_disparity=0,
+                        max_disparity=wl["D"] - 1)
+    lf, rf = l.astype(np.float32), r.astype(np.float32)
+    best = 1e30
+    for _ in range(2):
+        t = time.perf_counter()
+        O.run(cfg, lf, rf, want=("out",))
+        best = min(best, time.perf_counter() - t)
+    return {"value": 1.0 / best, "unit": "frames/s", "cores": O.num_threads(), "kind": "port",
+            "sample": f"1 frame of {wl['name']} (best of 2), oracle/stereo_oracle.c with OpenMP over all host cores"}
+
+
+def run_ours(args):
+    import torch
+    from stereo_depth_b200 import backend, cuda_depth
+    rank, world, local = dist_setup(args)
+    wl = WORKLOADS[args.workload]
+    H, W, K, D = wl["H"], wl["W"], wl["K"], wl["D"]
+    F = args.frames
+    cfg = cuda_depth.StereoMatchingConfiguration(height=H, width=W, downscale_factor=K, min_disparity=0,
+                                                 max_disparity=D - 1)
+    be = backend.CudaStereoMatchingBackend(cfg, frames_per_launch=args.frames_per_launch)
+    sm = be.native
+    Hd, Wd, L = sm.dims
+    lh, rh = make_inputs(wl, F, args.distinct, rank)
+    lh, rh = lh.pin_memory(), rh.pin_memory()
+    ld, rd = lh.cuda(), rh.cuda()
+    out_d = torch.empty((F, H, W), dtype=torch.float32, device="cuda")
+    out_h = torch.empty((F, H, W), dtype=torch.float32).pin_memory()
+    in_bytes = 2 * F * 3 * H * W
+    out_bytes = F * H * W * 4
+
+    # ---- device-resident throughput ----------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        sm.compute_disparity_batch(ld, rd, out=out_d)
+    sampler = ClockSampler(local)
+    barrier(world)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(world)
+    e0.record()
+    for _ in range(args.steps):
+        sm.compute_disparity_batch(ld, rd, out=out_d)
+    e1.record()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * F * args.steps / (ms * 1e-3)
+
+    # ---- end to end from pinned host memory through the plugin API ---------------------------------
+    for _ in range(2):
+        be.process_batch(lh, rh, out=out_h)
+    barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        be.process_batch(lh, rh, out=out_h)   # synchronous: returns when out_h is complete
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+    barrier(world)
+    e2e = world * F * args.steps / e2e_s
+    same = bool(torch.equal(out_h[:2], out_d[:2].cpu()))
+
+    # ---- per-kernel device times (CUDA events inside the library, on the launching stream) ----------
+    sm.profile(True)
+    for _ in range(2):
+        sm.compute_disparity_batch(ld, rd, out=out_d)
+    prof = sm.profile_read()
+    sm.profile(False)
+    b_ms, b_n = prof["cost_agg_wta"]
+    frames_per_launch = sm.frames_per_launch
+    ops_per_launch = 237.0 * Hd * Wd * L * frames_per_launch           # 237 lane-ops per cell
+    achieved = ops_per_launch / (b_ms / b_n * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "kernelB_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload)
+        except (OSError, ValueError):
+            traffic = None
+    kernel_ms = {k: round(v[0] / max(v[1], 1), 4) for k, v in prof.items()}
+    total_prof = sum(v[0] for v in prof.values())
+
+    if rank != 0:
+        return
+    line = {
+        "metric": "frames/s", "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['name']}, {F} frames per GPU per step, frame-sharded",
+                   "H": H, "W": W, "D": D, "K": K, "frames_per_gpu_per_step": F, "input": "uint8 CHW",
+                   "frames_per_launch": frames_per_launch, "distinct_frames": min(args.distinct, F),
+                   "l2": f"inputs {in_bytes / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
+                   "parallelism": f"frame-batch x{world}, no collective"},
+        "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": in_bytes,
+                "d2h_bytes_per_step": out_bytes, "api": "CudaStereoMatchingBackend.process_batch (sd_compute_host)",
+                "timer": "wall clock around the synchronous call, max over ranks", "matches_device_path": same},
+        "gpu_launches": sm.launches_per_call(F) * args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "fp32_alu", "kernel": "mbm_wta_fast_kernel (fused cost + aggregation + WTA)",
+                     "achieved": round(achieved, 3), "peak": FADD_PEAK_TOPS, "unit": "TFLOP/s",
+                     "frac": round(achieved / FADD_PEAK_TOPS, 4), "traffic": traffic,
+                     "peak_source": "measured fp32 add peak of the CUDA cores (128 lane-adds/clk/SM x 148 SM x 1.955 GHz, "
+                                    "tools/microbench/fadd_bench; MEASURED_PEAKS.json has no ALU figure); 1 lane-op = 1 'FLOP'",
+                     "algorithmic_ops_per_launch": ops_per_launch, "launch_ms": round(b_ms / b_n, 4),
+                     "share_of_step": round(b_ms / total_prof, 4), "kernel_ms_per_launch": kernel_ms},
+    }
+    if world == 1 and not args.no_extras:
+        try:
+            line["cpu_baseline"] = cpu_baseline_leg(wl)
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"error": str(e)[:200]}
+        line["reference_cuda"] = reference_subprocess(args, frames=4, steps=3)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm
+# ------------------------------------------------------------------------------------------------
+
+def load_reference_module():
+    import importlib.util
+    import torch  # noqa: F401  (libtorch symbols must be loaded first)
+    path = os.path.join(ROOT, "oracle", "_ref", "cuda_depth.so")
+    if not os.path.exists(path):
+        return None
+    spec = importlib.util.spec_from_file_location("cuda_depth", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def run_reference_gpu(args, wl):
+    """The reference's own CUDA kernels (unmodified algorithm; sm_100 build of a patched copy, see
+    oracle/build_ref.py) through its public class cuda_depth.StereoMatching."""
+    import torch
+    mod = load_reference_module()
+    if mod is None:
+        return None
+    H, W, K, D = wl["H"], wl["W"], wl["K"], wl["D"]
+    F = min(args.frames, 8)
+    torch.cuda.set_device(0)
+    lh, rh = make_inputs(wl, F, min(args.distinct, F), 0)
+    lh, rh = lh.pin_memory(), rh.pin_memory()
+    # one large cached segment so the reference's out-of-bounds reads stay inside mapped memory
+    # and keep a pre-guard at its start: secondary_matching reads up to 5 rows BEFORE left_grayscaled
+    guard = torch.empty(2 << 30, dtype=torch.uint8, device="cuda")
+    del guard
+    pre_guard = torch.zeros(64 << 20, dtype=torch.uint8, device="cuda")  # noqa: F841  (carved from the cached 2 GiB block)
+    sm = mod.StereoMatching(mod.StereoMatchingConfiguration(height=H, width=W, downscale_factor=K, min_disparity=0,
+                                                            max_disparity=D - 1))
+    lf = [lh[i].cuda().float().contiguous() for i in range(F)]
+    rf = [rh[i].cuda().float().contiguous() for i in range(F)]
+
+    def step():
+        for i in range(F):
+            sm.compute_disparity_map(lf[i], rf[i])
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    value = F * args.steps / (ms * 1e-3)
+    # end to end as CudaStereoMatchingBackend.process does it (cuda_stereo_matching_backend.py:13-17) + D2H
+    out_h = torch.empty((H, W), dtype=torch.float32).pin_memory()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for i in range(F):
+            o = sm.compute_disparity_map(lh[i].cuda().float().contiguous(), rh[i].cuda().float().contiguous())
+            out_h.copy_(o)
+    torch.cuda.synchronize()
+    e2e = F * args.steps / (time.perf_counter() - t0)
+    return {"value": value, "ms_per_step": ms / args.steps, "e2e": e2e, "frames": F,
+            "h2d": 2 * F * 3 * H * W, "d2h": F * H * W * 4}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the reference arm
+    wl = WORKLOADS[args.workload]
+    base = {"metric": "frames/s", "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference",
+            "config": {"workload": f"{args.workload}: {wl['name']}", "H": wl["H"], "W": wl["W"], "D": wl["D"], "K": wl["K"]}}
+    res = None
+    try:
+        import torch
+        if torch.cuda.is_available():
+            res = run_reference_gpu(args, wl)
+    except Exception as e:  # noqa: BLE001
+        base["reference_gpu_error"] = str(e)[:300]
+    if res is not None:
+        base.update({"value": round(res["value"], 2), "ms_per_step": round(res["ms_per_step"], 3),
+                     "config": dict(base["config"], frames_per_step=res["frames"], input="float32 CHW on device",
+                                    device="the reference's own CUDA kernels on 1 B200 (it has no CPU or multi-GPU path)"),
+                     "cpu_baseline": {"value": round(res["value"], 2), "unit": "frames/s", "cores": 0, "kind": "reference",
+                                      "sample": f"{res['frames']} frames per step, reference CUDA kernels (oracle/_ref/cuda_depth.so) "
+                                                "on one B200; cores=0: runs on the GPU, not on host cores"},
+                     "e2e": {"value": round(res["e2e"], 2), "unit": "frames/s", "h2d_bytes_per_step": res["h2d"],
+                             "d2h_bytes_per_step": res["d2h"],
+                             "api": "uint8 host -> .cuda().float().contiguous() -> compute_disparity_map -> host"}})
+    else:
+        cb = cpu_baseline_leg(wl)
+        cb["kind"] = "port"
+        base.update({"value": round(cb["value"], 4), "ms_per_step": round(1000.0 / cb["value"], 1), "cpu_baseline": cb,
+                     "e2e": {"value": round(cb["value"], 4), "unit": "frames/s", "h2d_bytes_per_step": 0,
+                             "d2h_bytes_per_step": 0}})
+    print(json.dumps(base), flush=True)
+
+
+def reference_subprocess(args, frames, steps):
+    """Times the reference CUDA kernels in a child process (its out-of-bounds reads must not be able to
+    take this process's CUDA context down) and returns the parsed result."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload,
+           "--frames", str(frames), "--steps", str(steps), "--warmup", "1"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env).stdout.strip().splitlines()
+        j = json.loads(out[-1])
+        return {"value": j.get("value"), "unit": "frames/s", "e2e": j.get("e2e", {}).get("value"),
+                "kind": j.get("cpu_baseline", {}).get("kind"), "sample": j.get("cpu_baseline", {}).get("sample")}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:200]}
+
+
+def main():
+    args = parse_args()
+    if args.gpus > 1 and "RANK" not in os.environ:
+        import socket
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

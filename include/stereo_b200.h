@@ -111,6 +111,13 @@ int sd_set_variant(sd_handle *h, int variant);
 int sd_launches_per_call(sd_handle *h, int n_frames);
 
 int sd_frames_per_launch(sd_handle *h);
+
+/* Per-kernel device timing for benchmarks: while enabled, sd_compute brackets each of its four
+ * kernels (0 gray+pool, 1 cost+aggregation+WTA, 2 secondary matching, 3 upscale+fill) with CUDA
+ * events on the launching stream.  sd_profile_read waits for the last event, returns the summed
+ * milliseconds and launch counts per kernel ([4] each) since the previous read, and resets them. */
+int sd_profile_enable(sd_handle *h, int on);
+int sd_profile_read(sd_handle *h, double *ms_per_kernel, int *launches_per_kernel);
 const char *sd_last_error(sd_handle *h);
 int sd_last_cuda_error(sd_handle *h);
 

@@ -19,7 +19,8 @@ CONFIG_FIELDS = ("height", "width", "downscale_factor", "min_disparity", "max_di
 # every symbol include/stereo_b200.h declares
 EXPORTS = ("sd_abi_version", "sd_config_default", "sd_dims", "sd_create", "sd_destroy", "sd_compute",
            "sd_compute_host", "sd_get_stage", "sd_set_debug_volumes", "sd_set_variant",
-           "sd_launches_per_call", "sd_frames_per_launch", "sd_last_error", "sd_last_cuda_error")
+           "sd_launches_per_call", "sd_frames_per_launch", "sd_profile_enable", "sd_profile_read",
+           "sd_last_error", "sd_last_cuda_error")
 
 
 class SdConfig(C.Structure):
@@ -60,6 +61,8 @@ def lib():
     L.sd_set_variant.argtypes = [vp, ip]
     L.sd_launches_per_call.argtypes = [vp, ip]
     L.sd_frames_per_launch.argtypes = [vp]
+    L.sd_profile_enable.argtypes = [vp, ip]
+    L.sd_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.sd_last_error.argtypes = [vp]
     L.sd_last_error.restype = C.c_char_p
     L.sd_last_cuda_error.argtypes = [vp]
@@ -119,6 +122,15 @@ class Handle:
 
     def launches_per_call(self, n_frames):
         return lib().sd_launches_per_call(self._h, n_frames)
+
+    def profile_enable(self, on=True):
+        self.check(lib().sd_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self):
+        ms, n = (C.c_double * 4)(), (C.c_int * 4)()
+        self.check(lib().sd_profile_read(self._h, ms, n))
+        names = ("gray_pool", "cost_agg_wta", "secondary", "fill")
+        return {k: (ms[i], n[i]) for i, k in enumerate(names)}
 
     @property
     def frames_per_launch(self):

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 
@@ -29,6 +30,9 @@ struct sd_handle {
     void *din_l[kSlots], *din_r[kSlots];
     float *dout[kSlots];
     cudaEvent_t ev_h2d[kSlots], ev_comp[kSlots], ev_d2h[kSlots];
+    // optional per-kernel timing (sd_profile_enable): 5 events per chunk on the launching stream
+    bool prof;
+    std::vector<cudaEvent_t> *prof_events;
     char err[320];
     int last_cuda;
 };
@@ -101,13 +105,28 @@ __global__ void extract_agg3(const float4 *__restrict__ w, const float2 *__restr
     dst[3 * i + 2] = (bd == L - 1) ? ed.x : v.w;
 }
 
+int prof_mark(sd_handle *h, cudaStream_t st) {
+    if (!h->prof) return SD_OK;
+    cudaEvent_t e;
+    SD_CUDA(h, cudaEventCreate(&e));
+    SD_CUDA(h, cudaEventRecord(e, st));
+    h->prof_events->push_back(e);
+    return SD_OK;
+}
+
 int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int frames, float *out, cudaStream_t st) {
+    int rc;
+    if ((rc = prof_mark(h, st)) != SD_OK) return rc;
     SD_CUDA(h, launch_gray_pool(h->g, left, right, dtype, frames, h->s, st));
+    if ((rc = prof_mark(h, st)) != SD_OK) return rc;
     const bool fast = (h->variant == 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g));
     if (fast) SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
     else SD_CUDA(h, launch_mbm_wta_generic(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
+    if ((rc = prof_mark(h, st)) != SD_OK) return rc;
     SD_CUDA(h, launch_secondary(h->g, frames, h->s, st));
+    if ((rc = prof_mark(h, st)) != SD_OK) return rc;
     SD_CUDA(h, launch_fill(h->g, frames, h->s, out, st));
+    if ((rc = prof_mark(h, st)) != SD_OK) return rc;
     return SD_OK;
 }
 
@@ -180,6 +199,8 @@ int sd_create(const sd_config *cfg, int device, int frames_per_launch, sd_handle
     if (!h) return SD_ERR_NOMEM;
     memset(h, 0, sizeof(*h));
     *out = h;  // returned even on failure so the caller can read sd_last_error, then sd_destroy
+    h->prof_events = new (std::nothrow) std::vector<cudaEvent_t>();
+    if (!h->prof_events) return fail(h, SD_ERR_NOMEM, "out of host memory");
     h->cfg = *cfg;
     h->device = device;
     if (const char *why = validate(cfg)) return fail(h, SD_ERR_BAD_ARG, why);
@@ -228,6 +249,10 @@ int sd_destroy(sd_handle *h) {
         cudaFree(h->s.wta4);
         cudaFree(h->s.edge2);
         cudaFree(h->s.refined);
+        if (h->prof_events) {
+            for (cudaEvent_t e : *h->prof_events) cudaEventDestroy(e);
+            delete h->prof_events;
+        }
     }
     delete h;
     return SD_OK;
@@ -345,6 +370,34 @@ int sd_launches_per_call(sd_handle *h, int n_frames) {
 }
 
 int sd_frames_per_launch(sd_handle *h) { return h ? h->chunk : 0; }
+
+int sd_profile_enable(sd_handle *h, int on) {
+    if (!h) return SD_ERR_BAD_ARG;
+    h->prof = on != 0;
+    return SD_OK;
+}
+
+int sd_profile_read(sd_handle *h, double *ms, int *launches) {
+    if (!h || !ms || !launches) return SD_ERR_BAD_ARG;
+    DeviceGuard dg(h->device);
+    std::vector<cudaEvent_t> &ev = *h->prof_events;
+    for (int k = 0; k < 4; k++) {
+        ms[k] = 0.0;
+        launches[k] = 0;
+    }
+    if (!ev.empty()) SD_CUDA(h, cudaEventSynchronize(ev.back()));
+    for (size_t i = 0; i + 4 < ev.size(); i += 5) {
+        for (int k = 0; k < 4; k++) {
+            float t = 0.f;
+            SD_CUDA(h, cudaEventElapsedTime(&t, ev[i + k], ev[i + k + 1]));
+            ms[k] += t;
+            launches[k] += 1;
+        }
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    ev.clear();
+    return SD_OK;
+}
 
 const char *sd_last_error(sd_handle *h) { return h ? h->err : "null handle"; }
 

@@ -15,11 +15,17 @@
 //     in shared memory once per tile and reused by all L/2 passes;
 //   * the 3x3 cost is computed by row-streaming 4-column strips: every |L-R| tap is evaluated once and
 //     reused by the 3 cost rows and up to 3 cost columns that contain it;
-//   * WTA state (best, d*, A[d*-1], A[d*+1], previous level) stays in registers; the volume never exists.
+//   * WTA keeps only (best, previous level) in registers and rewrites a pixel's 16-byte record
+//     (d*, A[d*-1], A[d*], A[d*+1]) when its maximum improves; the [Hd,Wd,L] volume never exists.
 //
 // Semantics: identical to mbm_wta_generic.cu / oracle so_cost + so_aggregate + so_wta (SAFE padding).
 // References: device_functions.cuh:53-73, ncc_matching_cost_volume_construction.cu:67-76,
 // multi_block_matching_cost_aggregation.cu:56-87, wta_disparity_selection.cu:22-30.
+#include <cuda_pipeline.h>
+#include <stdlib.h>
+
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace sd {
@@ -58,7 +64,7 @@ __device__ __forceinline__ float tap(float l, float r) { return __fsub_rn(255.0f
 // Shared-memory position (in 16 B chunks) of logical chunk q within a cost-plane row.
 __device__ __forceinline__ constexpr int chunk_pos(int q) { return (q >> 1) + (q & 1) * HALF; }
 
-template <int BH, bool DBG>
+template <int BH, bool DBG, int MODE>
 __global__ void __launch_bounds__(Cfg<BH>::NT, (BH <= 32) ? 2 : 1)
 mbm_wta_fast_kernel(Geom g, const float *__restrict__ pool, float4 *__restrict__ wta4, float2 *__restrict__ edge2,
                     int RW, float *__restrict__ dbg_cost, float *__restrict__ dbg_agg) {
@@ -76,37 +82,50 @@ mbm_wta_fast_kernel(Geom g, const float *__restrict__ pool, float4 *__restrict__
     const float *pl = pool + (size_t)frame * 2 * np, *pr = pl + np;
 
     // ---- stage the pooled row bands once per tile (circular padding applied here) ----------------
+    // cp.async (LDGSTS): every element is in flight at once instead of one exposed L2 round trip each.
     {
         const int warp = tid >> 5, lane = tid & 31, nwarps = C::NT / 32;
         const int originR = c0 - 10 - g.min_ds - Lp;  // virtual column of bandR[.][0]
         for (int rr = warp; rr < C::BR; rr += nwarps) {
             const size_t ro = (size_t)wrapm(r0 - 11 + rr, Hd) * Wd;
-            for (int cc = lane; cc < LW; cc += 32) bandL[rr * LW + cc] = __ldg(pl + ro + wrapm(c0 - 11 + cc, Wd));
-            for (int cc = lane; cc < RW; cc += 32) bandR[rr * RW + cc] = __ldg(pr + ro + wrapm(originR + cc, Wd));
+            for (int cc = lane; cc < LW; cc += 32)
+                __pipeline_memcpy_async(&bandL[rr * LW + cc], pl + ro + wrapm(c0 - 11 + cc, Wd), 4);
+            for (int cc = lane; cc < RW; cc += 32)
+                __pipeline_memcpy_async(&bandR[rr * RW + cc], pr + ro + wrapm(originR + cc, Wd), 4);
         }
+        __pipeline_commit();
     }
 
     // ---- per-pixel WTA state (16 pixels, index k = a*4 + b) ---------------------------------------
-    float best[16], am1[16], ap1[16], prev[16];
-    int bd[16];
+    // Only the running maximum and the previous level stay in registers.  Whenever a pixel's maximum
+    // improves, its record (d*, A[d*-1], A[d*], A[d*+1]) is (re)written to HBM/L2 -- about ln(L) times per
+    // pixel -- which keeps ~50 registers free for the adder chains.  Pixels outside the image start at
+    // +inf and therefore never store.
+    const int px0 = r0 + 4 * ty, py0 = c0 + 4 * tx;  // first owned pixel
+    const size_t o00 = (size_t)frame * np + (size_t)px0 * Wd + py0;
+    float best[16], prev[16];
+    unsigned pend = 0;  // bit k: record k still waits for A[d*+1] (arrives with the next pass)
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        best[k] = kFltMin;
-        am1[k] = ap1[k] = prev[k] = 0.0f;
-        bd[k] = 0;
+        const bool valid = (px0 + (k >> 2) < Hd) && (py0 + (k & 3) < Wd);
+        best[k] = valid ? kFltMin : __int_as_float(0x7f800000);
+        prev[k] = 0.0f;
     }
-    const int px0 = r0 + 4 * ty, py0 = c0 + 4 * tx;  // first owned pixel
 
     // cost-phase work item of this thread
     const bool has_item = tid < C::ITEMS;
     const int strip = tid % NSTRIP, seg = tid / NSTRIP;
 
+    __pipeline_wait_prior(0);
     __syncthreads();
 
     for (int m = 0; m < M; m++) {
         const int d0 = 2 * m;
         // ================= cost phase: plane[R][s] = (cost(d0), cost(d0+1)) ==========================
-        if (has_item) {
+        // The right band is read at column offset e = Lp-2-d0 (even): 16-byte aligned on every other
+        // pass.  Two straight-line variants keep every load at its widest conflict-free form.
+        auto cost_phase = [&](auto aligned_tag) {
+            constexpr bool ALIGNED = decltype(aligned_tag)::value;
             const int R0 = seg * SEG;
             const float *bl = bandL + R0 * LW + strip * 4;
             const float *br = bandR + R0 * RW + strip * 4 + (Lp - 2 - d0);
@@ -114,12 +133,20 @@ mbm_wta_fast_kernel(Geom g, const float *__restrict__ pool, float4 *__restrict__
             auto taps = [&](int brow, float2(&t)[6]) {
                 const float4 l4 = *reinterpret_cast<const float4 *>(bl + brow * LW);
                 const float2 l2 = *reinterpret_cast<const float2 *>(bl + brow * LW + 4);
-                const float2 ra = *reinterpret_cast<const float2 *>(br + brow * RW);
-                const float2 rb = *reinterpret_cast<const float2 *>(br + brow * RW + 2);
-                const float2 rc = *reinterpret_cast<const float2 *>(br + brow * RW + 4);
-                const float2 rd = *reinterpret_cast<const float2 *>(br + brow * RW + 6);
+                float rv[8];
+                if (ALIGNED) {
+                    const float4 q0 = *reinterpret_cast<const float4 *>(br + brow * RW);
+                    const float4 q1 = *reinterpret_cast<const float4 *>(br + brow * RW + 4);
+                    rv[0] = q0.x; rv[1] = q0.y; rv[2] = q0.z; rv[3] = q0.w;
+                    rv[4] = q1.x; rv[5] = q1.y; rv[6] = q1.z; rv[7] = q1.w;
+                } else {
+                    const float2 ra = *reinterpret_cast<const float2 *>(br + brow * RW);
+                    const float4 q = *reinterpret_cast<const float4 *>(br + brow * RW + 2);
+                    const float2 rd = *reinterpret_cast<const float2 *>(br + brow * RW + 6);
+                    rv[0] = ra.x; rv[1] = ra.y; rv[2] = q.x; rv[3] = q.y;
+                    rv[4] = q.z; rv[5] = q.w; rv[6] = rd.x; rv[7] = rd.y;
+                }
                 const float lv[6] = {l4.x, l4.y, l4.z, l4.w, l2.x, l2.y};
-                const float rv[8] = {ra.x, ra.y, rb.x, rb.y, rc.x, rc.y, rd.x, rd.y};
 #pragma unroll
                 for (int j = 0; j < 6; j++) t[j] = make_float2(tap(lv[j], rv[j + 1]), tap(lv[j], rv[j]));
             };
@@ -131,30 +158,36 @@ mbm_wta_fast_kernel(Geom g, const float *__restrict__ pool, float4 *__restrict__
                 float2(&mid)[6] = T[(rr + 1) % 3];
                 float2(&bot)[6] = T[(rr + 2) % 3];
                 taps(rr + 2, bot);
+                // four independent 9-tap chains, interleaved; (0.0f + x) + y == x + y exactly
                 float2 c[4];
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    float2 s = top[i];  // 0.0f + x == x: the chain's first add is exact
-                    s = __fadd2_rn(s, top[i + 1]);
-                    s = __fadd2_rn(s, top[i + 2]);
-                    s = __fadd2_rn(s, mid[i]);
-                    s = __fadd2_rn(s, mid[i + 1]);
-                    s = __fadd2_rn(s, mid[i + 2]);
-                    s = __fadd2_rn(s, bot[i]);
-                    s = __fadd2_rn(s, bot[i + 1]);
-                    s = __fadd2_rn(s, bot[i + 2]);
-                    c[i] = s;
-                }
+                for (int i = 0; i < 4; i++) c[i] = __fadd2_rn(top[i], top[i + 1]);
+#pragma unroll
+                for (int i = 0; i < 4; i++) c[i] = __fadd2_rn(c[i], top[i + 2]);
+#pragma unroll
+                for (int q = 0; q < 3; q++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) c[i] = __fadd2_rn(c[i], mid[i + q]);
+#pragma unroll
+                for (int q = 0; q < 3; q++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) c[i] = __fadd2_rn(c[i], bot[i + q]);
                 const int R = R0 + rr;
                 if (R < C::PRW) {
                     plane[R * NCHUNK + strip] = make_float4(c[0].x, c[0].y, c[1].x, c[1].y);
                     plane[R * NCHUNK + HALF + strip] = make_float4(c[2].x, c[2].y, c[3].x, c[3].y);
                 }
             }
+        };
+        if (has_item) {
+            if (((Lp - 2 - d0) & 3) == 0) cost_phase(std::true_type{});
+            else cost_phase(std::false_type{});
         }
         __syncthreads();
 
         // ================= aggregation phase ==========================================================
+        // Loop nests put the tap index outermost and the 16 pixels innermost: consecutive instructions
+        // belong to independent chains, while each chain still adds its taps in (row, col) order.
         float2 hv[16], acc[16];
         // ---- H: 3 rows x 21 cols.  plane rows 4ty+9 .. 4ty+14, cells 4tx .. 4tx+23 -----------------------
         {
@@ -169,21 +202,20 @@ mbm_wta_fast_kernel(Geom g, const float *__restrict__ pool, float4 *__restrict__
                     v[2 * j + 1] = hi2(q);
                 }
 #pragma unroll
-                for (int a = 0; a < 4; a++) {
-                    const int rel = t - 1 - a;  // window row offset of plane row t for pixel row a
-                    if (rel < -1 || rel > 1) continue;
+                for (int j = 0; j < 21; j++) {
 #pragma unroll
-                    for (int b = 0; b < 4; b++) {
+                    for (int a = 0; a < 4; a++) {
+                        const int rel = t - 1 - a;  // window row offset of plane row t for pixel row a
+                        if (rel < -1 || rel > 1) continue;
+                        if (rel == -1 && j == 0) continue;  // folded into j == 1
 #pragma unroll
-                        for (int j = 0; j < 21; j++) {
-                            if (rel == -1 && j == 0) acc[a * 4 + b] = v[b];
-                            else acc[a * 4 + b] = __fadd2_rn(acc[a * 4 + b], v[b + j]);
+                        for (int b = 0; b < 4; b++) {
+                            if (rel == -1 && j == 1) hv[a * 4 + b] = __fadd2_rn(v[b], v[b + 1]);
+                            else hv[a * 4 + b] = __fadd2_rn(hv[a * 4 + b], v[b + j]);
                         }
                     }
                 }
             }
-#pragma unroll
-            for (int k = 0; k < 16; k++) hv[k] = acc[k];
         }
         // ---- V: 21 rows x 3 cols.  plane rows 4ty .. 4ty+23, cells 4tx+8 .. 4tx+15 (uses +9..+14) -----
         {
@@ -193,14 +225,16 @@ mbm_wta_fast_kernel(Geom g, const float *__restrict__ pool, float4 *__restrict__
                 const float4 q0 = p[0], q1 = p[HALF], q2 = p[1], q3 = p[HALF + 1];
                 const float2 w[8] = {lo2(q0), hi2(q0), lo2(q1), hi2(q1), lo2(q2), hi2(q2), lo2(q3), hi2(q3)};
 #pragma unroll
-                for (int a = 0; a < 4; a++) {
-                    if (a < amin || a > amax) continue;
+                for (int c3 = 0; c3 < 3; c3++) {
 #pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        if (a == first_a) acc[a * 4 + b] = w[b + 1];
-                        else acc[a * 4 + b] = __fadd2_rn(acc[a * 4 + b], w[b + 1]);
-                        acc[a * 4 + b] = __fadd2_rn(acc[a * 4 + b], w[b + 2]);
-                        acc[a * 4 + b] = __fadd2_rn(acc[a * 4 + b], w[b + 3]);
+                    for (int a = 0; a < 4; a++) {
+                        if (a < amin || a > amax) continue;
+                        if (a == first_a && c3 == 0) continue;  // folded into c3 == 1
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            if (a == first_a && c3 == 1) acc[a * 4 + b] = __fadd2_rn(w[b + 1], w[b + 2]);
+                            else acc[a * 4 + b] = __fadd2_rn(acc[a * 4 + b], w[b + 1 + c3]);
+                        }
                     }
                 }
             };
@@ -208,9 +242,35 @@ mbm_wta_fast_kernel(Geom g, const float *__restrict__ pool, float4 *__restrict__
             vrow(vp + 1 * NCHUNK, 0, 1, 1);
             vrow(vp + 2 * NCHUNK, 0, 2, 2);
             vrow(vp + 3 * NCHUNK, 0, 3, 3);
-            const float4 *p = vp + 4 * NCHUNK;
+            if ((MODE & 3) == 1) {
+#pragma unroll
+                for (int t = 4; t <= 20; t++) vrow(vp + t * NCHUNK, 0, 3, -1);
+            } else if ((MODE & 3) == 2) {
+                // manual software pipeline: the next row's loads are issued before this row's adds
+                auto vload = [&](const float4 *p, float4(&q)[4]) { q[0] = p[0]; q[1] = p[HALF]; q[2] = p[1]; q[3] = p[HALF + 1]; };
+                auto vcomp = [&](const float4(&q)[4]) {
+                    const float2 w[8] = {lo2(q[0]), hi2(q[0]), lo2(q[1]), hi2(q[1]), lo2(q[2]), hi2(q[2]), lo2(q[3]), hi2(q[3])};
+#pragma unroll
+                    for (int c3 = 0; c3 < 3; c3++)
+#pragma unroll
+                        for (int k = 0; k < 16; k++) acc[k] = __fadd2_rn(acc[k], w[(k & 3) + 1 + c3]);
+                };
+                float4 qa[4], qb[4];
+                const float4 *p = vp + 4 * NCHUNK;
+                vload(p, qa);
+#pragma unroll 1
+                for (int t = 4; t < 20; t += 2, p += 2 * NCHUNK) {
+                    vload(p + NCHUNK, qb);
+                    vcomp(qa);
+                    vload(p + 2 * NCHUNK, qa);
+                    vcomp(qb);
+                }
+                vcomp(qa);  // row 20
+            } else {
+                const float4 *p = vp + 4 * NCHUNK;
 #pragma unroll 2
-            for (int t = 4; t <= 20; t++, p += NCHUNK) vrow(p, 0, 3, -1);
+                for (int t = 4; t <= 20; t++, p += NCHUNK) vrow(p, 0, 3, -1);
+            }
             vrow(vp + 21 * NCHUNK, 1, 3, -1);
             vrow(vp + 22 * NCHUNK, 2, 3, -1);
             vrow(vp + 23 * NCHUNK, 3, 3, -1);
@@ -226,13 +286,14 @@ mbm_wta_fast_kernel(Geom g, const float *__restrict__ pool, float4 *__restrict__
                 const float2 u[12] = {lo2(q0), hi2(q0), lo2(q1), hi2(q1), lo2(q2), hi2(q2),
                                       lo2(q3), hi2(q3), lo2(q4), hi2(q4), lo2(q5), hi2(q5)};
 #pragma unroll
-                for (int a = 0; a < 4; a++) {
-                    if (a < amin || a > amax) continue;
+                for (int j = 0; j < 9; j++) {
 #pragma unroll
-                    for (int b = 0; b < 4; b++) {
+                    for (int a = 0; a < 4; a++) {
+                        if (a < amin || a > amax) continue;
+                        if (a == first_a && j == 0) continue;  // folded into j == 1
 #pragma unroll
-                        for (int j = 0; j < 9; j++) {
-                            if (a == first_a && j == 0) acc[a * 4 + b] = u[b];
+                        for (int b = 0; b < 4; b++) {
+                            if (a == first_a && j == 1) acc[a * 4 + b] = __fadd2_rn(u[b], u[b + 1]);
                             else acc[a * 4 + b] = __fadd2_rn(acc[a * 4 + b], u[b + j]);
                         }
                     }
@@ -242,9 +303,14 @@ mbm_wta_fast_kernel(Geom g, const float *__restrict__ pool, float4 *__restrict__
             crow(cp + 1 * NCHUNK, 0, 1, 1);
             crow(cp + 2 * NCHUNK, 0, 2, 2);
             crow(cp + 3 * NCHUNK, 0, 3, 3);
-            const float4 *p = cp + 4 * NCHUNK;
+            if (MODE & 4) {
+#pragma unroll
+                for (int t = 4; t <= 8; t++) crow(cp + t * NCHUNK, 0, 3, -1);
+            } else {
+                const float4 *p = cp + 4 * NCHUNK;
 #pragma unroll 1
-            for (int t = 4; t <= 8; t++, p += NCHUNK) crow(p, 0, 3, -1);
+                for (int t = 4; t <= 8; t++, p += NCHUNK) crow(p, 0, 3, -1);
+            }
             crow(cp + 9 * NCHUNK, 1, 3, -1);
             crow(cp + 10 * NCHUNK, 2, 3, -1);
             crow(cp + 11 * NCHUNK, 3, 3, -1);
@@ -275,51 +341,65 @@ mbm_wta_fast_kernel(Geom g, const float *__restrict__ pool, float4 *__restrict__
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 const int x = px0 + (k >> 2), y = py0 + (k & 3);
-                if (x < Hd && y < Wd) edge2[(size_t)frame * np + (size_t)x * Wd + y].x = hv[k].x;  // A[0]
+                if (x < Hd && y < Wd) {
+                    const size_t o = o00 + (size_t)(k >> 2) * Wd + (k & 3);
+                    edge2[o].x = hv[k].x;                                    // A[0]
+                    wta4[o] = make_float4(0.0f, 0.0f, hv[k].x, hv[k].y);      // record if nothing ever beats FLT_MIN
+                }
             }
         }
         const bool has2 = (d0 + 1 < L);
+        const float fd0 = (float)d0, fd1 = (float)(d0 + 1);
+        unsigned npend = 0;
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             const float a0 = hv[k].x, a1 = hv[k].y;
-            if (bd[k] == d0 - 1) ap1[k] = a0;
+            float4 *rec = wta4 + o00 + (size_t)(k >> 2) * Wd + (k & 3);
+            if (pend & (1u << k)) rec->w = a0;  // A[d*+1] for a maximum found at d0-1
             if (a0 > best[k]) {
                 best[k] = a0;
-                bd[k] = d0;
-                am1[k] = prev[k];
+                *rec = make_float4(fd0, prev[k], a0, a1);
             }
-            if (bd[k] == d0) ap1[k] = a1;
             if (has2 && a1 > best[k]) {
                 best[k] = a1;
-                bd[k] = d0 + 1;
-                am1[k] = a0;
+                *rec = make_float4(fd1, a0, a1, 0.0f);
+                npend |= 1u << k;
             }
             prev[k] = has2 ? a1 : a0;
         }
+        pend = npend;
         __syncthreads();  // everyone is done reading the plane before the next pass overwrites it
     }
 
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         const int x = px0 + (k >> 2), y = py0 + (k & 3);
-        if (x < Hd && y < Wd) {
-            const size_t o = (size_t)frame * np + (size_t)x * Wd + y;
-            wta4[o] = make_float4((float)bd[k], am1[k], best[k], ap1[k]);
-            edge2[o].y = prev[k];  // A[L-1]
-        }
+        if (x < Hd && y < Wd) edge2[o00 + (size_t)(k >> 2) * Wd + (k & 3)].y = prev[k];  // A[L-1]
     }
 }
 
-template <int BH, bool DBG>
+template <int BH, bool DBG, int MODE>
 cudaError_t launch_t(const Geom &g, int frames, const Scratch &s, float *dbg_cost, float *dbg_agg, cudaStream_t st) {
     const size_t smem = smem_bytes<BH>(g.L);
     // per-device attribute: set on every launch (cheap) so multi-GPU processes stay correct
-    cudaError_t e = cudaFuncSetAttribute(mbm_wta_fast_kernel<BH, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mbm_wta_fast_kernel<BH, DBG, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((g.Wd + BW - 1) / BW, (g.Hd + BH - 1) / BH, frames);
-    mbm_wta_fast_kernel<BH, DBG><<<grid, Cfg<BH>::NT, smem, st>>>(g, s.pool, s.wta4, s.edge2, right_band_pitch(g.L),
-                                                                   dbg_cost, dbg_agg);
+    mbm_wta_fast_kernel<BH, DBG, MODE><<<grid, Cfg<BH>::NT, smem, st>>>(g, s.pool, s.wta4, s.edge2, right_band_pitch(g.L),
+                                                                         dbg_cost, dbg_agg);
     return cudaGetLastError();
+}
+
+int fast_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        // tuning knob.  bits 0-1: V loop 0 rolled (unroll 2), 1 fully unrolled, 2 manual software pipeline;
+        // bit 2: C loop fully unrolled.
+        const char *e = getenv("SD_FAST_MODE");
+        mode = e ? atoi(e) : 0;
+        if (mode < 0 || mode > 6 || (mode & 3) == 3) mode = 0;
+    }
+    return mode;
 }
 
 }  // namespace
@@ -331,8 +411,15 @@ bool mbm_wta_fast_supported(const Geom &g) {
 cudaError_t launch_mbm_wta_fast(const Geom &g, int frames, const Scratch &s, float *dbg_cost, float *dbg_agg,
                                 cudaStream_t st) {
     if (!mbm_wta_fast_supported(g)) return cudaErrorNotSupported;
-    if (dbg_cost || dbg_agg) return launch_t<32, true>(g, frames, s, dbg_cost, dbg_agg, st);
-    return launch_t<32, false>(g, frames, s, dbg_cost, dbg_agg, st);
+    if (dbg_cost || dbg_agg) return launch_t<32, true, 0>(g, frames, s, dbg_cost, dbg_agg, st);
+    switch (fast_mode()) {
+        case 1: return launch_t<32, false, 1>(g, frames, s, dbg_cost, dbg_agg, st);
+        case 2: return launch_t<32, false, 2>(g, frames, s, dbg_cost, dbg_agg, st);
+        case 4: return launch_t<32, false, 4>(g, frames, s, dbg_cost, dbg_agg, st);
+        case 5: return launch_t<32, false, 5>(g, frames, s, dbg_cost, dbg_agg, st);
+        case 6: return launch_t<32, false, 6>(g, frames, s, dbg_cost, dbg_agg, st);
+        default: return launch_t<32, false, 0>(g, frames, s, dbg_cost, dbg_agg, st);
+    }
 }
 
 }  // namespace sd

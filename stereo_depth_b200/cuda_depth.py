@@ -157,6 +157,13 @@ class StereoMatching:
     def set_variant(self, v):
         self._handle.set_variant({"auto": 0, "generic": 1, "fast": 2}.get(v, v))
 
+    def profile(self, on=True):
+        self._handle.profile_enable(on)
+
+    def profile_read(self):
+        """{kernel: (milliseconds, launches)} accumulated since the last read (device time, CUDA events)."""
+        return self._handle.profile_read()
+
     def launches_per_call(self, n_frames=1):
         return self._handle.launches_per_call(n_frames)
 

@@ -34,7 +34,11 @@ for name in names:
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / (reps * nf)
+        sm.profile(True)
+        sm.compute_disparity_batch(l, r, out=out)
+        prof = {k: round(v[0] / nf, 4) for k, v in sm.profile_read().items()}
+        sm.profile(False)
         Hd, Wd, L = sm.dims
         ops = 237.0 * Hd * Wd * L
         print(f"{name} {variant}: {ms:.4f} ms/frame  {1000/ms:.1f} fps  (kernel-B algorithmic {ops/1e9:.2f} Gop -> "
-              f"{ops/ms/1e9:.1f} Top/s if B were everything)", flush=True)
+              f"{ops/ms/1e9:.1f} Top/s if B were everything)  per-frame kernel ms: {prof}  B: {ops/prof['cost_agg_wta']/1e9:.1f} Top/s", flush=True)
