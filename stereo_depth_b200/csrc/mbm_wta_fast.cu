@@ -396,8 +396,8 @@ int fast_mode() {
         // tuning knob.  bits 0-1: V loop 0 rolled (unroll 2), 1 fully unrolled, 2 manual software pipeline;
         // bit 2: C loop fully unrolled.
         const char *e = getenv("SD_FAST_MODE");
-        mode = e ? atoi(e) : 0;
-        if (mode < 0 || mode > 6 || (mode & 3) == 3) mode = 0;
+        mode = e ? atoi(e) : 2;
+        if (mode < 0 || mode > 6 || (mode & 3) == 3) mode = 2;
     }
     return mode;
 }

@@ -61,15 +61,83 @@ __global__ void __launch_bounds__(128) secondary_kernel(Geom g, const float *__r
     if (KT > 0) {
 #pragma unroll
         for (int k = 0; k < NC; k++) S[k] = 0.0f;
-        for (int i = -r; i <= r; i++) {
-            const size_t ro = (size_t)wrapm(x * K + i, H) * W;
-            for (int j = -r; j <= r; j++) {
-                const int c = y * K + j;
-                const float l = __ldg(gl + ro + wrapm(c, W));
+        // Tap (j, k) reads GL[c+j] and GR[c+j-(lo+k)] = GR[base + (j-k+KT)] with base = c - KT*dm:
+        // per image row only 2r+1 left and 2r+2KT+1 right values are distinct.  RS = sad radius when it
+        // is the reference default (registers), otherwise fall through to the per-tap loads below.
+        constexpr int RS = 5, NL = 2 * RS + 1, NR = 2 * RS + 2 * KT + 1;
+        const int c = y * K, base = c - K * dm;
+        const bool interior = (r == RS) && (x * K - RS >= 0) && (x * K + RS < H) && (c - RS >= 0) && (c + RS < W) &&
+                              (base - RS - KT >= 0) && (base + RS + KT < W);
+        if (KT == 2 && interior && (W & 1) == 0 && c - RS - 1 >= 0 && base - RS - KT - 1 >= 0) {
+            // K = 2: the first needed column is odd for both views; start one earlier and use 8-byte loads
+            // (adjacent lanes are 8 bytes apart: every LDG.64 is fully coalesced).
+            const float2 *lp = reinterpret_cast<const float2 *>(gl + (size_t)(x * K - RS) * W + (c - RS - 1));
+            const float2 *rp = reinterpret_cast<const float2 *>(gr + (size_t)(x * K - RS) * W + (base - RS - KT - 1));
+            const int pitch2 = W >> 1;
+#pragma unroll 1
+            for (int i = 0; i < NL; i++, lp += pitch2, rp += pitch2) {
+                float lv[NL + 1], rv[NR + 1];
 #pragma unroll
-                for (int k = 0; k < NC; k++) {
-                    const float rr = __ldg(gr + ro + wrapm(c - (lo + k), W));
-                    S[k] = __fadd_rn(S[k], __fsub_rn(255.0f, fabsf(__fsub_rn(l, rr))));
+                for (int j = 0; j < (NL + 1) / 2; j++) {
+                    const float2 t = __ldg(lp + j);
+                    lv[2 * j] = t.x;
+                    lv[2 * j + 1] = t.y;
+                }
+#pragma unroll
+                for (int q = 0; q < (NR + 1) / 2; q++) {
+                    const float2 t = __ldg(rp + q);
+                    rv[2 * q] = t.x;
+                    rv[2 * q + 1] = t.y;
+                }
+#pragma unroll
+                for (int j = 0; j < NL; j++)
+#pragma unroll
+                    for (int k = 0; k < NC; k++)
+                        S[k] = __fadd_rn(S[k], __fsub_rn(255.0f, fabsf(__fsub_rn(lv[j + 1], rv[j - k + 2 * KT + 1]))));
+            }
+        } else if (interior) {
+            const float *lp = gl + (size_t)(x * K - RS) * W + (c - RS);
+            const float *rp = gr + (size_t)(x * K - RS) * W + (base - RS - KT);
+#pragma unroll 1
+            for (int i = 0; i < NL; i++, lp += W, rp += W) {
+                float lv[NL], rv[NR];
+#pragma unroll
+                for (int j = 0; j < NL; j++) lv[j] = __ldg(lp + j);
+#pragma unroll
+                for (int q = 0; q < NR; q++) rv[q] = __ldg(rp + q);
+#pragma unroll
+                for (int j = 0; j < NL; j++)
+#pragma unroll
+                    for (int k = 0; k < NC; k++)
+                        S[k] = __fadd_rn(S[k], __fsub_rn(255.0f, fabsf(__fsub_rn(lv[j], rv[j - k + 2 * KT]))));
+            }
+        } else if (r == RS) {
+            // border pixels: same register-blocked structure, every index wrapped (SAFE modulo padding)
+#pragma unroll 1
+            for (int i = 0; i < NL; i++) {
+                const size_t ro = (size_t)wrapm(x * K - RS + i, H) * W;
+                float lv[NL], rv[NR];
+#pragma unroll
+                for (int j = 0; j < NL; j++) lv[j] = __ldg(gl + ro + wrapm(c - RS + j, W));
+#pragma unroll
+                for (int q = 0; q < NR; q++) rv[q] = __ldg(gr + ro + wrapm(base - RS - KT + q, W));
+#pragma unroll
+                for (int j = 0; j < NL; j++)
+#pragma unroll
+                    for (int k = 0; k < NC; k++)
+                        S[k] = __fadd_rn(S[k], __fsub_rn(255.0f, fabsf(__fsub_rn(lv[j], rv[j - k + 2 * KT]))));
+            }
+        } else {
+            for (int i = -r; i <= r; i++) {
+                const size_t ro = (size_t)wrapm(x * K + i, H) * W;
+                for (int j = -r; j <= r; j++) {
+                    const int cc = y * K + j;
+                    const float l = __ldg(gl + ro + wrapm(cc, W));
+#pragma unroll
+                    for (int k = 0; k < NC; k++) {
+                        const float rr = __ldg(gr + ro + wrapm(cc - (lo + k), W));
+                        S[k] = __fadd_rn(S[k], __fsub_rn(255.0f, fabsf(__fsub_rn(l, rr))));
+                    }
                 }
             }
         }
