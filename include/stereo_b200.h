@@ -86,6 +86,20 @@ int sd_destroy(sd_handle *h);
 int sd_compute(sd_handle *h, const void *left, const void *right, int dtype, int n_frames,
                float *out, void *cuda_stream);
 
+/* Runs only kernels first_kernel..last_kernel (0 gray+pool, 1 cost+aggregation+WTA, 2 secondary matching,
+ * 3 upscale+fill) of one chunk (n_frames <= frames_per_launch), so a caller can place a collective between
+ * stages.  Used by the row-band mode: kernel 0, all-gather of the left gray bands over NCCL, kernels 1..3. */
+int sd_compute_range(sd_handle *h, const void *left, const void *right, int dtype, int n_frames,
+                     float *out, void *cuda_stream, int first_kernel, int last_kernel);
+
+/* Row-band mode for a single very large frame split across GPUs (no reference counterpart: the
+ * reference is single-GPU).  The handle's image is a window of `global_height` rows of a larger image:
+ * local pooled row 0 is global pooled row `pooled_row_offset` (may be negative: circular).  The
+ * vertical/horizontal fill then applies the reference's row rules (upscale_disparity_vertical_fill.cu:26-31,
+ * horizontal_disparity_fill.cu:26-27) with GLOBAL row numbers and reads its colour reference row from
+ * `global_left_gray` ([global_height, W] floats, device).  global_height <= 0 switches back to normal mode. */
+int sd_set_band(sd_handle *h, int pooled_row_offset, int global_height, const float *global_left_gray);
+
 /* Same computation with HOST buffers (pinned memory recommended): host->device copies, the
  * kernels and device->host copies are pipelined over internal streams, chunk by chunk.
  * Synchronous: returns when `out` is complete.  This is the end-to-end call

@@ -18,7 +18,7 @@ CONFIG_FIELDS = ("height", "width", "downscale_factor", "min_disparity", "max_di
 
 # every symbol include/stereo_b200.h declares
 EXPORTS = ("sd_abi_version", "sd_config_default", "sd_dims", "sd_create", "sd_destroy", "sd_compute",
-           "sd_compute_host", "sd_get_stage", "sd_set_debug_volumes", "sd_set_variant",
+           "sd_compute_range", "sd_set_band", "sd_compute_host", "sd_get_stage", "sd_set_debug_volumes", "sd_set_variant",
            "sd_launches_per_call", "sd_frames_per_launch", "sd_profile_enable", "sd_profile_read",
            "sd_last_error", "sd_last_cuda_error")
 
@@ -56,6 +56,8 @@ def lib():
     L.sd_destroy.argtypes = [vp]
     L.sd_compute.argtypes = [vp, vp, vp, ip, ip, vp, vp]
     L.sd_compute_host.argtypes = [vp, vp, vp, ip, ip, vp]
+    L.sd_compute_range.argtypes = [vp, vp, vp, ip, ip, vp, vp, ip, ip]
+    L.sd_set_band.argtypes = [vp, ip, ip, vp]
     L.sd_get_stage.argtypes = [vp, ip, ip, vp, vp]
     L.sd_set_debug_volumes.argtypes = [vp, vp, vp]
     L.sd_set_variant.argtypes = [vp, ip]
@@ -107,6 +109,12 @@ class Handle:
 
     def compute(self, left_ptr, right_ptr, dtype, n_frames, out_ptr, stream_ptr):
         self.check(lib().sd_compute(self._h, left_ptr, right_ptr, dtype, n_frames, out_ptr, stream_ptr))
+
+    def compute_range(self, left_ptr, right_ptr, dtype, n_frames, out_ptr, stream_ptr, first, last):
+        self.check(lib().sd_compute_range(self._h, left_ptr, right_ptr, dtype, n_frames, out_ptr, stream_ptr, first, last))
+
+    def set_band(self, pooled_row_offset, global_height, global_left_gray_ptr):
+        self.check(lib().sd_set_band(self._h, pooled_row_offset, global_height, global_left_gray_ptr))
 
     def compute_host(self, left_ptr, right_ptr, dtype, n_frames, out_ptr):
         self.check(lib().sd_compute_host(self._h, left_ptr, right_ptr, dtype, n_frames, out_ptr))

@@ -23,6 +23,7 @@ struct sd_handle {
     int variant;     // 0 auto, 1 generic, 2 fast
     Scratch s;
     float *dbg_cost, *dbg_agg;
+    const float *gl_glob;  // band mode: left gray of the global image (device), else NULL
     // host pipeline (lazily created by sd_compute_host)
     bool host_ready;
     int host_dtype;
@@ -114,19 +115,23 @@ int prof_mark(sd_handle *h, cudaStream_t st) {
     return SD_OK;
 }
 
-int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int frames, float *out, cudaStream_t st) {
+int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int frames, float *out, cudaStream_t st,
+              int k0 = 0, int k1 = 3) {
     int rc;
-    if ((rc = prof_mark(h, st)) != SD_OK) return rc;
-    SD_CUDA(h, launch_gray_pool(h->g, left, right, dtype, frames, h->s, st));
-    if ((rc = prof_mark(h, st)) != SD_OK) return rc;
-    const bool fast = (h->variant == 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g));
-    if (fast) SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
-    else SD_CUDA(h, launch_mbm_wta_generic(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
-    if ((rc = prof_mark(h, st)) != SD_OK) return rc;
-    SD_CUDA(h, launch_secondary(h->g, frames, h->s, st));
-    if ((rc = prof_mark(h, st)) != SD_OK) return rc;
-    SD_CUDA(h, launch_fill(h->g, frames, h->s, out, st));
-    if ((rc = prof_mark(h, st)) != SD_OK) return rc;
+    const bool full = (k0 == 0 && k1 == 3);  // per-kernel profiling only brackets complete passes
+    if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
+    if (k0 <= 0 && 0 <= k1) SD_CUDA(h, launch_gray_pool(h->g, left, right, dtype, frames, h->s, st));
+    if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
+    if (k0 <= 1 && 1 <= k1) {
+        const bool fast = (h->variant == 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g));
+        if (fast) SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
+        else SD_CUDA(h, launch_mbm_wta_generic(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
+    }
+    if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
+    if (k0 <= 2 && 2 <= k1) SD_CUDA(h, launch_secondary(h->g, frames, h->s, st));
+    if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
+    if (k0 <= 3 && 3 <= k1) SD_CUDA(h, launch_fill(h->g, frames, h->s, h->gl_glob, out, st));
+    if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
     return SD_OK;
 }
 
@@ -216,6 +221,9 @@ int sd_create(const sd_config *cfg, int device, int frames_per_launch, sd_handle
     g.rm = cfg->mid_mbm_radius;
     g.rl = cfg->large_mbm_radius;
     g.threshold = (float)cfg->threshold;
+    g.band_x_off = 0;
+    g.Hd_glob = g.Hd;
+    g.H_glob = g.H;
     if (frames_per_launch <= 0) {
         // default: keep one chunk's working set (gray+pooled+outputs) well inside the 126 MB L2
         const size_t per_frame = (size_t)g.H * g.W * 4 * 3 + (size_t)g.Hd * g.Wd * 36;
@@ -273,6 +281,38 @@ int sd_compute(sd_handle *h, const void *left, const void *right, int dtype, int
                                  out + outn * f0, st);
         if (rc != SD_OK) return rc;
     }
+    return SD_OK;
+}
+
+int sd_compute_range(sd_handle *h, const void *left, const void *right, int dtype, int n_frames, float *out,
+                     void *stream, int first_kernel, int last_kernel) {
+    if (!h) return SD_ERR_BAD_ARG;
+    if (first_kernel < 0 || last_kernel > 3 || first_kernel > last_kernel) return fail(h, SD_ERR_BAD_ARG, "kernel range must be within [0,3]");
+    if (first_kernel == 0 && (!left || !right)) return fail(h, SD_ERR_BAD_ARG, "null image pointer");
+    if (last_kernel == 3 && !out) return fail(h, SD_ERR_BAD_ARG, "null output pointer");
+    if (dtype != SD_U8 && dtype != SD_F32) return fail(h, SD_ERR_SHAPE, "dtype must be SD_U8 or SD_F32");
+    if (n_frames <= 0 || n_frames > h->chunk) return fail(h, SD_ERR_SHAPE, "sd_compute_range handles at most frames_per_launch frames");
+    DeviceGuard dg(h->device);
+    if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
+    return run_chunk(h, left, right, dtype, n_frames, out, (cudaStream_t)stream, first_kernel, last_kernel);
+}
+
+int sd_set_band(sd_handle *h, int pooled_row_offset, int global_height, const float *global_left_gray) {
+    if (!h) return SD_ERR_BAD_ARG;
+    const int K = h->g.K;
+    if (global_height <= 0) {  // back to normal mode
+        h->g.band_x_off = 0;
+        h->g.Hd_glob = h->g.Hd;
+        h->g.H_glob = h->g.H;
+        h->gl_glob = nullptr;
+        return SD_OK;
+    }
+    if (global_height % K != 0 || h->g.H % K != 0) return fail(h, SD_ERR_UNSUPPORTED, "band mode needs heights divisible by downscale_factor");
+    if (!global_left_gray) return fail(h, SD_ERR_BAD_ARG, "band mode needs the global left gray image");
+    h->g.band_x_off = pooled_row_offset;
+    h->g.H_glob = global_height;
+    h->g.Hd_glob = global_height / K;
+    h->gl_glob = global_left_gray;
     return SD_OK;
 }
 

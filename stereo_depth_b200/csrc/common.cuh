@@ -29,6 +29,10 @@ struct Geom {
     int r_sad;         // sad_patch_radius
     int rs, rm, rl;    // small / mid / large multi-block radii
     float threshold;
+    // Row-band mode (single very large frame split over GPUs, bands.py): this handle processes a window of
+    // the global image.  band_x_off = global pooled row of local pooled row 0 (may be negative: circular),
+    // Hd_glob / H_glob = global heights.  Normal mode: 0, Hd, H.
+    int band_x_off, Hd_glob, H_glob;
 };
 
 // Per-chunk scratch in HBM (frame-major; one chunk = frames_per_launch frames).
@@ -54,6 +58,6 @@ bool mbm_wta_fast_supported(const Geom &g);
 cudaError_t launch_mbm_wta_fast(const Geom &g, int frames, const Scratch &s, float *dbg_cost,
                                 float *dbg_agg, cudaStream_t st);
 cudaError_t launch_secondary(const Geom &g, int frames, const Scratch &s, cudaStream_t st);
-cudaError_t launch_fill(const Geom &g, int frames, const Scratch &s, float *out, cudaStream_t st);
+cudaError_t launch_fill(const Geom &g, int frames, const Scratch &s, const float *gl_glob, float *out, cudaStream_t st);
 
 }  // namespace sd

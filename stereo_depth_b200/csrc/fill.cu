@@ -20,17 +20,19 @@
 namespace sd {
 namespace {
 
-__device__ __forceinline__ float vfill_value(const Geom &g, const float *__restrict__ gl,
+// gl = left gray of this handle's (local) image; glg = left gray of the GLOBAL image (== gl outside band mode).
+__device__ __forceinline__ float vfill_value(const Geom &g, const float *__restrict__ gl, const float *__restrict__ glg,
                                              const float *__restrict__ disp, int r, int c) {
     const int K = g.K, x = r / K, i = r - x * K, yd = c / K;
     const float fk = (float)K;
     const float p = __fmul_rn(fk, __ldg(disp + (size_t)x * g.Wd + yd));
-    if (i == 0 || x == 0) return p;
+    const int xg = wrapm(x + g.band_x_off, g.Hd_glob);  // global pooled row (the reference's x)
+    if (i == 0 || xg == 0 || x == 0) return p;
     const float n = __fmul_rn(fk, __ldg(disp + (size_t)(x - 1) * g.Wd + yd));
     if (fabsf(__fsub_rn(p, n)) <= g.threshold)
         return __fadd_rn(p, __fdiv_rn(__fmul_rn((float)i, __fsub_rn(n, p)), fk));
     const float prev_color = __ldg(gl + (size_t)(K * x) * g.W + c);
-    const float next_color = __ldg(gl + (size_t)wrapm((K + 1) * x, g.H) * g.W + c);
+    const float next_color = __ldg(glg + (size_t)wrapm((K + 1) * xg, g.H_glob) * g.W + c);
     const float cur = __ldg(gl + (size_t)r * g.W + c);
     return (fabsf(__fsub_rn(cur, prev_color)) <= fabsf(__fsub_rn(cur, next_color))) ? p : n;
 }
@@ -49,14 +51,16 @@ __device__ __forceinline__ float hfill_value(const Geom &g, const float *__restr
 }
 
 // value of the "next" mod-K sample to the right of nk on row r
-__device__ __forceinline__ float next_sample(const Geom &g, const float *__restrict__ gl,
+__device__ __forceinline__ float next_sample(const Geom &g, const float *__restrict__ gl, const float *__restrict__ glg,
                                              const float *__restrict__ disp, int r, int nk, float p) {
-    if (nk + g.K < g.W) return vfill_value(g, gl, disp, r, nk + g.K);
-    if (g.W % g.K == 0 && r + 1 < g.H) return vfill_value(g, gl, disp, r + 1, 0);
+    if (nk + g.K < g.W) return vfill_value(g, gl, glg, disp, r, nk + g.K);
+    // the reference's flat index lands on column 0 of the next row -- unless this is the GLOBAL last row
+    const int rg = wrapm(r + g.band_x_off * g.K, g.H_glob);
+    if (g.W % g.K == 0 && rg + 1 < g.H_glob && r + 1 < g.H) return vfill_value(g, gl, glg, disp, r + 1, 0);
     return p;
 }
 
-__global__ void __launch_bounds__(256) fill_kernel(Geom g, const float *__restrict__ gray,
+__global__ void __launch_bounds__(256) fill_kernel(Geom g, const float *__restrict__ gray, const float *__restrict__ gl_glob,
                                                    const float *__restrict__ refined, float *__restrict__ out, bool vec_ok) {
     const int c4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int r = blockIdx.y * blockDim.y + threadIdx.y;
@@ -64,6 +68,7 @@ __global__ void __launch_bounds__(256) fill_kernel(Geom g, const float *__restri
     if (r >= g.H || c4 >= g.W) return;
     const size_t plane = (size_t)g.H * g.W;
     const float *gl = gray + (size_t)frame * 2 * plane;
+    const float *glg = gl_glob ? gl_glob : gl;
     const float *disp = refined + (size_t)frame * g.Hd * g.Wd;
     float *o = out + (size_t)frame * plane + (size_t)r * g.W + c4;
     float v[4];
@@ -75,8 +80,8 @@ __global__ void __launch_bounds__(256) fill_kernel(Geom g, const float *__restri
         if (c >= g.W) break;
         const int nk = c - c % g.K;
         if (nk != nk_cached) {
-            p = (nk_cached >= 0 && nk == nk_cached + g.K) ? n : vfill_value(g, gl, disp, r, nk);
-            n = next_sample(g, gl, disp, r, nk, p);
+            p = (nk_cached >= 0 && nk == nk_cached + g.K) ? n : vfill_value(g, gl, glg, disp, r, nk);
+            n = next_sample(g, gl, glg, disp, r, nk, p);
             nk_cached = nk;
         }
         v[k] = hfill_value(g, gl, r, c, nk, p, n);
@@ -90,10 +95,10 @@ __global__ void __launch_bounds__(256) fill_kernel(Geom g, const float *__restri
 
 }  // namespace
 
-cudaError_t launch_fill(const Geom &g, int frames, const Scratch &s, float *out, cudaStream_t st) {
+cudaError_t launch_fill(const Geom &g, int frames, const Scratch &s, const float *gl_glob, float *out, cudaStream_t st) {
     dim3 block(32, 8), grid(((g.W + 3) / 4 + 31) / 32, (g.H + 7) / 8, frames);
     const bool vec_ok = (g.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
-    fill_kernel<<<grid, block, 0, st>>>(g, s.gray, s.refined, out, vec_ok);
+    fill_kernel<<<grid, block, 0, st>>>(g, s.gray, gl_glob, s.refined, out, vec_ok);
     return cudaGetLastError();
 }
 
