@@ -65,7 +65,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={SMI_QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
@@ -252,7 +252,7 @@ def run_ours(args):
         "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": out_bytes, "api": "CudaStereoMatchingBackend.process_batch (sd_compute_host)",
                 "timer": "wall clock around the synchronous call, max over ranks", "matches_device_path": same},
-        "gpu_launches": sm.launches_per_call(F) * args.steps,
+        "gpu_launches": sm.launches_per_call(F) * args.steps * world,
         "clocks": clocks,
         "roofline": {"bound": "fp32_alu", "kernel": "mbm_wta_fast_kernel (fused cost + aggregation + WTA)",
                      "achieved": round(achieved, 3), "peak": FADD_PEAK_TOPS, "unit": "TFLOP/s",

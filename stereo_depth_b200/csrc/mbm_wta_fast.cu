@@ -59,6 +59,18 @@ __host__ __device__ inline size_t smem_bytes(int L) {
 
 __device__ __forceinline__ float2 lo2(const float4 &q) { return make_float2(q.x, q.y); }
 __device__ __forceinline__ float2 hi2(const float4 &q) { return make_float2(q.z, q.w); }
+// Shared-memory loads that the compiler keeps where they are written (volatile asm).
+__device__ __forceinline__ float4 lds128(const float *p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+}
+__device__ __forceinline__ float2 lds64(const float *p) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+}
 __device__ __forceinline__ float tap(float l, float r) { return __fsub_rn(255.0f, fabsf(__fsub_rn(l, r))); }
 
 // Shared-memory position (in 16 B chunks) of logical chunk q within a cost-plane row.
@@ -130,34 +142,48 @@ mbm_wta_fast_kernel(Geom g, const float *__restrict__ pool, float4 *__restrict__
             const float *bl = bandL + R0 * LW + strip * 4;
             const float *br = bandR + R0 * RW + strip * 4 + (Lp - 2 - d0);
             float2 T[3][6];
-            auto taps = [&](int brow, float2(&t)[6]) {
-                const float4 l4 = *reinterpret_cast<const float4 *>(bl + brow * LW);
-                const float2 l2 = *reinterpret_cast<const float2 *>(bl + brow * LW + 4);
-                float rv[8];
-                if (ALIGNED) {
-                    const float4 q0 = *reinterpret_cast<const float4 *>(br + brow * RW);
-                    const float4 q1 = *reinterpret_cast<const float4 *>(br + brow * RW + 4);
-                    rv[0] = q0.x; rv[1] = q0.y; rv[2] = q0.z; rv[3] = q0.w;
-                    rv[4] = q1.x; rv[5] = q1.y; rv[6] = q1.z; rv[7] = q1.w;
-                } else {
-                    const float2 ra = *reinterpret_cast<const float2 *>(br + brow * RW);
-                    const float4 q = *reinterpret_cast<const float4 *>(br + brow * RW + 2);
-                    const float2 rd = *reinterpret_cast<const float2 *>(br + brow * RW + 6);
-                    rv[0] = ra.x; rv[1] = ra.y; rv[2] = q.x; rv[3] = q.y;
-                    rv[4] = q.z; rv[5] = q.w; rv[6] = rd.x; rv[7] = rd.y;
-                }
-                const float lv[6] = {l4.x, l4.y, l4.z, l4.w, l2.x, l2.y};
-#pragma unroll
-                for (int j = 0; j < 6; j++) t[j] = make_float2(tap(lv[j], rv[j + 1]), tap(lv[j], rv[j]));
+            // Band loads are issued one full row ahead of their use through volatile asm (kept in program
+            // order by the compiler): the LDS latency then overlaps the previous row's taps and chains.
+            struct Raw {
+                float4 l4;
+                float2 l2;
+                float r[8];
             };
-            taps(0, T[0]);
-            taps(1, T[1]);
+            auto load_raw = [&](int brow) {
+                Raw w;
+                w.l4 = lds128(bl + brow * LW);
+                w.l2 = lds64(bl + brow * LW + 4);
+                if (ALIGNED) {
+                    const float4 q0 = lds128(br + brow * RW), q1 = lds128(br + brow * RW + 4);
+                    w.r[0] = q0.x; w.r[1] = q0.y; w.r[2] = q0.z; w.r[3] = q0.w;
+                    w.r[4] = q1.x; w.r[5] = q1.y; w.r[6] = q1.z; w.r[7] = q1.w;
+                } else {
+                    const float2 ra = lds64(br + brow * RW);
+                    const float4 q = lds128(br + brow * RW + 2);
+                    const float2 rd = lds64(br + brow * RW + 6);
+                    w.r[0] = ra.x; w.r[1] = ra.y; w.r[2] = q.x; w.r[3] = q.y;
+                    w.r[4] = q.z; w.r[5] = q.w; w.r[6] = rd.x; w.r[7] = rd.y;
+                }
+                return w;
+            };
+            auto taps = [&](const Raw &w, float2(&t)[6]) {
+                const float lv[6] = {w.l4.x, w.l4.y, w.l4.z, w.l4.w, w.l2.x, w.l2.y};
+#pragma unroll
+                for (int j = 0; j < 6; j++) t[j] = make_float2(tap(lv[j], w.r[j + 1]), tap(lv[j], w.r[j]));
+            };
+            Raw raw[2];
+            raw[0] = load_raw(0);
+            raw[1] = load_raw(1);
+            taps(raw[0], T[0]);
+            raw[0] = load_raw(2);
+            taps(raw[1], T[1]);
 #pragma unroll
             for (int rr = 0; rr < SEG; rr++) {
                 float2(&top)[6] = T[rr % 3];
                 float2(&mid)[6] = T[(rr + 1) % 3];
                 float2(&bot)[6] = T[(rr + 2) % 3];
-                taps(rr + 2, bot);
+                if (rr + 1 < SEG) raw[(rr + 1) & 1] = load_raw(rr + 3);  // next row's band values
+                taps(raw[rr & 1], bot);                                  // band row rr + 2
                 // four independent 9-tap chains, interleaved; (0.0f + x) + y == x + y exactly
                 float2 c[4];
 #pragma unroll
