@@ -117,6 +117,14 @@ int sd_get_stage(sd_handle *h, int stage, int frame, float *dst, void *cuda_stre
  * tensors the reference materialises (buffer/device_buffer.cc:9-10).  Pass NULLs to switch off. */
 int sd_set_debug_volumes(sd_handle *h, float *cost_volume, float *aggregated_volume);
 
+/* Reference-compat switch for min_disparity != 0.  The reference's secondary matching reads the aggregated
+ * volume at pad_index(ABSOLUTE disparity, L) with unchecked flat addressing (secondary_matching.cu:28-31), which
+ * for min_disparity/K != 0 is a different cell than the arg-max's neighbours (an upstream bug).  on = 1 (the
+ * default whenever min_disparity/K != 0): reproduce it bit for bit; this materialises the aggregated volume
+ * (frames_per_launch * Hd*Wd*L floats).  on = 0: use the relative index (what the algorithm intends; no volume).
+ * With min_disparity/K == 0 both are identical and no volume is ever allocated unless on = 1 is forced. */
+int sd_set_compat(sd_handle *h, int on);
+
 /* Selects the fused-kernel variant: 0 = auto, 1 = generic (any radii), 2 = specialised
  * (radii 1/4/10, cost radius 1).  SD_ERR_UNSUPPORTED if the configuration does not allow it. */
 int sd_set_variant(sd_handle *h, int variant);

@@ -12,8 +12,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libstereo_oracle.so")
 
-MODE_SAFE = 0
-MODE_REF = 1
+MODE_SAFE = 0     # SAFE padding, relative index into the aggregated volume
+MODE_COMPAT = 2   # SAFE padding + the reference's absolute-index read (differs only when min_disparity != 0)
+MODE_REF = 3      # additionally emulates the reference's in-tensor aliased reads
 
 CONFIG_FIELDS = ("height", "width", "downscale_factor", "min_disparity", "max_disparity",
                  "ncc_patch_radius", "sad_patch_radius", "threshold",

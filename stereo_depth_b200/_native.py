@@ -18,7 +18,7 @@ CONFIG_FIELDS = ("height", "width", "downscale_factor", "min_disparity", "max_di
 
 # every symbol include/stereo_b200.h declares
 EXPORTS = ("sd_abi_version", "sd_config_default", "sd_dims", "sd_create", "sd_destroy", "sd_compute",
-           "sd_compute_range", "sd_set_band", "sd_compute_host", "sd_get_stage", "sd_set_debug_volumes", "sd_set_variant",
+           "sd_compute_range", "sd_set_band", "sd_compute_host", "sd_get_stage", "sd_set_debug_volumes", "sd_set_compat", "sd_set_variant",
            "sd_launches_per_call", "sd_frames_per_launch", "sd_profile_enable", "sd_profile_read",
            "sd_last_error", "sd_last_cuda_error")
 
@@ -61,6 +61,7 @@ def lib():
     L.sd_get_stage.argtypes = [vp, ip, ip, vp, vp]
     L.sd_set_debug_volumes.argtypes = [vp, vp, vp]
     L.sd_set_variant.argtypes = [vp, ip]
+    L.sd_set_compat.argtypes = [vp, ip]
     L.sd_launches_per_call.argtypes = [vp, ip]
     L.sd_frames_per_launch.argtypes = [vp]
     L.sd_profile_enable.argtypes = [vp, ip]
@@ -124,6 +125,9 @@ class Handle:
 
     def set_debug_volumes(self, cost_ptr, agg_ptr):
         self.check(lib().sd_set_debug_volumes(self._h, cost_ptr, agg_ptr))
+
+    def set_compat(self, on):
+        self.check(lib().sd_set_compat(self._h, 1 if on else 0))
 
     def set_variant(self, v):
         self.check(lib().sd_set_variant(self._h, v))

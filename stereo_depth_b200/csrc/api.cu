@@ -124,8 +124,14 @@ int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int 
     if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
     if (k0 <= 1 && 1 <= k1) {
         const bool fast = (h->variant == 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g));
-        if (fast) SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
-        else SD_CUDA(h, launch_mbm_wta_generic(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
+        // reference-compat mode materialises the aggregated volume of every frame of the chunk
+        const bool all = h->s.agg_vol != nullptr;
+        float *agg_out = all ? h->s.agg_vol : h->dbg_agg;
+        if (fast) SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, agg_out, all, st));
+        else SD_CUDA(h, launch_mbm_wta_generic(h->g, frames, h->s, h->dbg_cost, agg_out, all, st));
+        if (all && h->dbg_agg)
+            SD_CUDA(h, cudaMemcpyAsync(h->dbg_agg, h->s.agg_vol, (size_t)h->g.Hd * h->g.Wd * h->g.L * sizeof(float),
+                                       cudaMemcpyDeviceToDevice, st));
     }
     if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
     if (k0 <= 2 && 2 <= k1) SD_CUDA(h, launch_secondary(h->g, frames, h->s, st));
@@ -178,6 +184,8 @@ int ensure_host_pipeline(sd_handle *h, int dtype) {
 }  // namespace
 
 extern "C" {
+
+int sd_set_compat(sd_handle *h, int on);
 
 int sd_abi_version(void) { return SD_ABI_VERSION; }
 
@@ -244,6 +252,24 @@ int sd_create(const sd_config *cfg, int device, int frames_per_launch, sd_handle
     SD_CUDA(h, cudaMalloc((void **)&h->s.wta4, F * nd * sizeof(float4)));
     SD_CUDA(h, cudaMalloc((void **)&h->s.edge2, F * nd * sizeof(float2)));
     SD_CUDA(h, cudaMalloc((void **)&h->s.refined, F * nd * sizeof(float)));
+    // The reference indexes the aggregated volume with the absolute disparity (secondary_matching.cu:28-31);
+    // with min_disparity/K != 0 that differs from the relative index, so reproduce it by default.
+    if (g.min_ds != 0) return sd_set_compat(h, 1);
+    return SD_OK;
+}
+
+int sd_set_compat(sd_handle *h, int on) {
+    if (!h) return SD_ERR_BAD_ARG;
+    DeviceGuard dg(h->device);
+    if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
+    if (on && !h->s.agg_vol) {
+        const size_t bytes = (size_t)h->chunk * h->g.Hd * h->g.Wd * h->g.L * sizeof(float);
+        SD_CUDA(h, cudaMalloc((void **)&h->s.agg_vol, bytes));
+    } else if (!on && h->s.agg_vol) {
+        SD_CUDA(h, cudaFree(h->s.agg_vol));
+        h->s.agg_vol = nullptr;
+    }
+    h->g.abs_index = on ? 1 : 0;
     return SD_OK;
 }
 
@@ -257,6 +283,7 @@ int sd_destroy(sd_handle *h) {
         cudaFree(h->s.wta4);
         cudaFree(h->s.edge2);
         cudaFree(h->s.refined);
+        cudaFree(h->s.agg_vol);
         if (h->prof_events) {
             for (cudaEvent_t e : *h->prof_events) cudaEventDestroy(e);
             delete h->prof_events;

@@ -21,6 +21,14 @@ __host__ __device__ __forceinline__ int wrapm(int i, int n) {
     return i < 0 ? i + n : i;
 }
 
+// The reference's pad_index, verbatim (device_functions.cuh:10-20): may return a NEGATIVE index.
+__host__ __device__ __forceinline__ int ref_pad_index(int index, int n) {
+    if (index >= 0 && index < n) return index;
+    if (index < 0) return n + index;
+    if (index == n) return 0;
+    return n - index;
+}
+
 // Geometry shared by all kernels of one handle.
 struct Geom {
     int H, W, K, Hd, Wd, L;
@@ -33,6 +41,9 @@ struct Geom {
     // the global image.  band_x_off = global pooled row of local pooled row 0 (may be negative: circular),
     // Hd_glob / H_glob = global heights.  Normal mode: 0, Hd, H.
     int band_x_off, Hd_glob, H_glob;
+    // 1: secondary matching indexes the aggregated volume with the ABSOLUTE disparity, like the reference
+    // (secondary_matching.cu:28-31).  Needs Scratch::agg_vol.  Default when min_disparity/K != 0.
+    int abs_index;
 };
 
 // Per-chunk scratch in HBM (frame-major; one chunk = frames_per_launch frames).
@@ -47,16 +58,17 @@ struct Scratch {
     float4 *wta4;
     float2 *edge2;
     float *refined;
+    float *agg_vol;  // [F][Hd][Wd][L] aggregated volume, only in reference-compat mode (abs_index), else NULL
 };
 
 // kernel launchers (each returns cudaGetLastError())
 cudaError_t launch_gray_pool(const Geom &g, const void *left, const void *right, int dtype, int frames,
                              const Scratch &s, cudaStream_t st);
 cudaError_t launch_mbm_wta_generic(const Geom &g, int frames, const Scratch &s, float *dbg_cost,
-                                   float *dbg_agg, cudaStream_t st);
+                                   float *dbg_agg, bool all_frames, cudaStream_t st);
 bool mbm_wta_fast_supported(const Geom &g);
 cudaError_t launch_mbm_wta_fast(const Geom &g, int frames, const Scratch &s, float *dbg_cost,
-                                float *dbg_agg, cudaStream_t st);
+                                float *dbg_agg, bool all_frames, cudaStream_t st);
 cudaError_t launch_secondary(const Geom &g, int frames, const Scratch &s, cudaStream_t st);
 cudaError_t launch_fill(const Geom &g, int frames, const Scratch &s, const float *gl_glob, float *out, cudaStream_t st);
 

@@ -79,7 +79,7 @@ __device__ __forceinline__ constexpr int chunk_pos(int q) { return (q >> 1) + (q
 template <int BH, bool DBG, int MODE>
 __global__ void __launch_bounds__(Cfg<BH>::NT, (BH <= 32) ? 2 : 1)
 mbm_wta_fast_kernel(Geom g, const float *__restrict__ pool, float4 *__restrict__ wta4, float2 *__restrict__ edge2,
-                    int RW, float *__restrict__ dbg_cost, float *__restrict__ dbg_agg) {
+                    int RW, float *__restrict__ dbg_cost, float *__restrict__ dbg_agg, int all_frames) {
     using C = Cfg<BH>;
     extern __shared__ float4 smem4[];
     float4 *plane = smem4;                                              // [PRW][42] chunks of (cell,level) pairs
@@ -345,7 +345,7 @@ mbm_wta_fast_kernel(Geom g, const float *__restrict__ pool, float4 *__restrict__
         }
 
         // ================= winner-take-all update (ascending d, strict >) =============================
-        if (DBG && frame == 0) {
+        if (DBG && (frame == 0 || all_frames)) {
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 const int x = px0 + (k >> 2), y = py0 + (k & 3);
@@ -354,11 +354,12 @@ mbm_wta_fast_kernel(Geom g, const float *__restrict__ pool, float4 *__restrict__
                     const float4 q = plane[R * NCHUNK + chunk_pos(s >> 1)];
                     const float2 cc = (s & 1) ? hi2(q) : lo2(q);
                     const size_t o = ((size_t)x * Wd + y) * L + d0;
-                    if (dbg_cost) dbg_cost[o] = cc.x;
-                    if (dbg_agg) dbg_agg[o] = hv[k].x;
+                    const size_t oa = (all_frames ? (size_t)frame * np * L : 0) + o;
+                    if (dbg_cost && frame == 0) dbg_cost[o] = cc.x;
+                    if (dbg_agg) dbg_agg[oa] = hv[k].x;
                     if (d0 + 1 < L) {
-                        if (dbg_cost) dbg_cost[o + 1] = cc.y;
-                        if (dbg_agg) dbg_agg[o + 1] = hv[k].y;
+                        if (dbg_cost && frame == 0) dbg_cost[o + 1] = cc.y;
+                        if (dbg_agg) dbg_agg[oa + 1] = hv[k].y;
                     }
                 }
             }
@@ -405,14 +406,15 @@ mbm_wta_fast_kernel(Geom g, const float *__restrict__ pool, float4 *__restrict__
 }
 
 template <int BH, bool DBG, int MODE>
-cudaError_t launch_t(const Geom &g, int frames, const Scratch &s, float *dbg_cost, float *dbg_agg, cudaStream_t st) {
+cudaError_t launch_t(const Geom &g, int frames, const Scratch &s, float *dbg_cost, float *dbg_agg, bool all_frames,
+                     cudaStream_t st) {
     const size_t smem = smem_bytes<BH>(g.L);
     // per-device attribute: set on every launch (cheap) so multi-GPU processes stay correct
     cudaError_t e = cudaFuncSetAttribute(mbm_wta_fast_kernel<BH, DBG, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((g.Wd + BW - 1) / BW, (g.Hd + BH - 1) / BH, frames);
     mbm_wta_fast_kernel<BH, DBG, MODE><<<grid, Cfg<BH>::NT, smem, st>>>(g, s.pool, s.wta4, s.edge2, right_band_pitch(g.L),
-                                                                         dbg_cost, dbg_agg);
+                                                                         dbg_cost, dbg_agg, all_frames ? 1 : 0);
     return cudaGetLastError();
 }
 
@@ -435,16 +437,16 @@ bool mbm_wta_fast_supported(const Geom &g) {
 }
 
 cudaError_t launch_mbm_wta_fast(const Geom &g, int frames, const Scratch &s, float *dbg_cost, float *dbg_agg,
-                                cudaStream_t st) {
+                                bool all_frames, cudaStream_t st) {
     if (!mbm_wta_fast_supported(g)) return cudaErrorNotSupported;
-    if (dbg_cost || dbg_agg) return launch_t<32, true, 0>(g, frames, s, dbg_cost, dbg_agg, st);
+    if (dbg_cost || dbg_agg) return launch_t<32, true, 0>(g, frames, s, dbg_cost, dbg_agg, all_frames, st);
     switch (fast_mode()) {
-        case 1: return launch_t<32, false, 1>(g, frames, s, dbg_cost, dbg_agg, st);
-        case 2: return launch_t<32, false, 2>(g, frames, s, dbg_cost, dbg_agg, st);
-        case 4: return launch_t<32, false, 4>(g, frames, s, dbg_cost, dbg_agg, st);
-        case 5: return launch_t<32, false, 5>(g, frames, s, dbg_cost, dbg_agg, st);
-        case 6: return launch_t<32, false, 6>(g, frames, s, dbg_cost, dbg_agg, st);
-        default: return launch_t<32, false, 0>(g, frames, s, dbg_cost, dbg_agg, st);
+        case 1: return launch_t<32, false, 1>(g, frames, s, dbg_cost, dbg_agg, false, st);
+        case 2: return launch_t<32, false, 2>(g, frames, s, dbg_cost, dbg_agg, false, st);
+        case 4: return launch_t<32, false, 4>(g, frames, s, dbg_cost, dbg_agg, false, st);
+        case 5: return launch_t<32, false, 5>(g, frames, s, dbg_cost, dbg_agg, false, st);
+        case 6: return launch_t<32, false, 6>(g, frames, s, dbg_cost, dbg_agg, false, st);
+        default: return launch_t<32, false, 0>(g, frames, s, dbg_cost, dbg_agg, false, st);
     }
 }
 

@@ -37,7 +37,8 @@ __device__ __forceinline__ float quad_peak(float x1, float y1, float x2, float y
 template <int KT>
 __global__ void __launch_bounds__(128) secondary_kernel(Geom g, const float *__restrict__ gray,
                                                         const float4 *__restrict__ wta4,
-                                                        const float2 *__restrict__ edge2, float *__restrict__ refined) {
+                                                        const float2 *__restrict__ edge2, const float *__restrict__ agg_vol,
+                                                        float *__restrict__ refined) {
     const int y = blockIdx.x * blockDim.x + threadIdx.x;
     const int x = blockIdx.y * blockDim.y + threadIdx.y;
     const int frame = blockIdx.z;
@@ -187,9 +188,22 @@ __global__ void __launch_bounds__(128) secondary_kernel(Geom g, const float *__r
             }
         }
         const float2 e = edge2[o];
-        const float a_d = (bd == 0) ? e.x : w.z;
-        const float a_m1 = (bd == 0) ? e.y : w.y;
-        const float a_p1 = (bd == g.L - 1) ? e.x : w.w;
+        float a_d = (bd == 0) ? e.x : w.z;
+        float a_m1 = (bd == 0) ? e.y : w.y;
+        float a_p1 = (bd == g.L - 1) ? e.x : w.w;
+        if (g.abs_index && agg_vol) {
+            // reference-compat: the reference reads agg[x][y][pad_index(ABSOLUTE disparity, L)] with unchecked flat
+            // addressing (secondary_matching.cu:28-31): a negative pad_index lands in the previous pixel's levels.
+            const size_t fb = (size_t)frame * g.Hd * g.Wd * g.L;
+            const long long po = ((long long)x * g.Wd + y) * g.L;
+            auto rd = [&](int q, float safe) {
+                const long long flat = po + ref_pad_index(q, g.L);
+                return flat >= 0 ? __ldg(agg_vol + fb + flat) : safe;  // before the tensor: SAFE (relative) value
+            };
+            a_d = rd(dm, a_d);
+            a_p1 = rd(dm + 1, a_p1);
+            a_m1 = rd(dm - 1, a_m1);
+        }
         const float fdm = (float)dm, fds = (float)d_sad, fk = (float)K;
         const float qm = quad_peak(fdm, a_d, (float)(dm + 1), a_p1, (float)(dm - 1), a_m1);
         const float qs = quad_peak(fds, c_sad, (float)(d_sad + 1), sp, (float)(d_sad - 1), sm);
@@ -208,11 +222,11 @@ __global__ void __launch_bounds__(128) secondary_kernel(Geom g, const float *__r
 cudaError_t launch_secondary(const Geom &g, int frames, const Scratch &s, cudaStream_t st) {
     dim3 block(32, 4), grid((g.Wd + 31) / 32, (g.Hd + 3) / 4, frames);
     switch (g.K) {
-        case 1: secondary_kernel<1><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.refined); break;
-        case 2: secondary_kernel<2><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.refined); break;
-        case 3: secondary_kernel<3><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.refined); break;
-        case 4: secondary_kernel<4><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.refined); break;
-        default: secondary_kernel<0><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.refined); break;
+        case 1: secondary_kernel<1><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.agg_vol, s.refined); break;
+        case 2: secondary_kernel<2><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.agg_vol, s.refined); break;
+        case 3: secondary_kernel<3><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.agg_vol, s.refined); break;
+        case 4: secondary_kernel<4><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.agg_vol, s.refined); break;
+        default: secondary_kernel<0><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.agg_vol, s.refined); break;
     }
     return cudaGetLastError();
 }

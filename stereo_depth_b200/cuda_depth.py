@@ -154,6 +154,10 @@ class StereoMatching:
         self._handle.set_debug_volumes(self._dbg[0].data_ptr(), self._dbg[1].data_ptr())
         return self._dbg
 
+    def set_compat(self, on=True):
+        """Reproduce (True) or fix (False) the reference's absolute-index read for min_disparity != 0."""
+        self._handle.set_compat(on)
+
     def set_variant(self, v):
         self._handle.set_variant({"auto": 0, "generic": 1, "fast": 2}.get(v, v))
 

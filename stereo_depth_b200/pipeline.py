@@ -1,0 +1,123 @@
+"""Thin shim of the reference's pipeline layer around the "cuda" backend, so the
+reference's scripts can run against this backend:
+
+  DepthEstimationPipelineConfig / Result / Context / DepthEstimationPipeline
+      <- src/python/pipeline/depth_estimation_pipeline.py:14-87
+  run_depth_estimation_pipeline
+      <- src/python/pipeline/depth_estimation_pipeline_runner.py:38-66
+
+Right-view synthesis (Deep3D) and the DNN backends are out of scope: `process` needs the right view, or a
+user-supplied `right_view_synthesis` object with a `.process(left)` method.
+"""
+from __future__ import annotations
+
+import time
+from contextlib import contextmanager
+from dataclasses import dataclass
+from typing import Any, Iterable, Optional, Tuple
+
+import torch
+
+from . import cuda_depth
+from .backend import CudaStereoMatchingBackend, StereoMatching
+
+
+@contextmanager
+def cuda_perf_clock(label: str, do_log: bool):
+    """helpers/torch_helpers.py:19-28: wall time with a device synchronisation, only when logging."""
+    if not do_log:
+        yield
+        return
+    torch.cuda.synchronize()
+    t0 = time.time()
+    yield
+    torch.cuda.synchronize()
+    print(f"{label}: {(time.time() - t0) * 1000:.3f} ms")
+
+
+@dataclass
+class DepthEstimationPipelineConfig:
+    image_shape: Tuple[int, int] = (384, 1280)
+    min_disparity: int = 1
+    max_disparity: int = 64
+    invalid_disparity: float = -1.0
+    stereo_matching_backend: str = "cuda"
+    log_perf_time: bool = False
+
+    def update(self, **kwargs: Any) -> "DepthEstimationPipelineConfig":
+        for key, value in kwargs.items():
+            if not hasattr(self, key):
+                raise RuntimeError(f"Unexpected keyword argument: '{key}'.")
+            setattr(self, key, value)
+        return self
+
+
+@dataclass
+class DepthEstimationResult:
+    left_image: torch.Tensor
+    right_image: torch.Tensor
+    disparity_map: torch.Tensor
+
+
+@dataclass
+class DepthEstimationPipelineContext:
+    disparity_map: torch.Tensor
+    left_image: torch.Tensor
+    right_image: torch.Tensor
+    config: DepthEstimationPipelineConfig
+    frame_index: int
+
+
+class DepthEstimationPipeline:
+
+    def __init__(self, config: Optional[DepthEstimationPipelineConfig] = None, right_view_synthesis=None):
+        self._config = config if config is not None else DepthEstimationPipelineConfig()
+        self._right_view_synthesis = right_view_synthesis
+        self._stereo_matching = self._get_stereo_matching()
+
+    def process(self, left_image: torch.Tensor, right_image: Optional[torch.Tensor] = None) -> DepthEstimationResult:
+        left_image = left_image.cuda()
+        with cuda_perf_clock("Right view generation", self._config.log_perf_time):
+            if right_image is None:
+                if self._right_view_synthesis is None:
+                    raise RuntimeError("right_image is required: right-view synthesis is outside this backend's scope "
+                                       "(pass right_view_synthesis= to plug one in)")
+                right_image = self._right_view_synthesis.process(left_image)
+        with cuda_perf_clock("Stereo matching", self._config.log_perf_time):
+            disparity_map = self._stereo_matching.process(left_image, right_image)
+        return DepthEstimationResult(disparity_map=disparity_map, left_image=left_image, right_image=right_image)
+
+    def get_configuration(self) -> DepthEstimationPipelineConfig:
+        return self._config
+
+    def _get_stereo_matching(self) -> StereoMatching:
+        if self._config.stereo_matching_backend == "cuda":
+            config = cuda_depth.StereoMatchingConfiguration(
+                height=self._config.image_shape[0],
+                width=self._config.image_shape[1],
+                min_disparity=self._config.min_disparity,
+                max_disparity=self._config.max_disparity,
+            )
+            return CudaStereoMatchingBackend(configuration=config)
+        raise RuntimeError(f"Unsupported stereo matching backend: {self._config.stereo_matching_backend}")
+
+
+def run_depth_estimation_pipeline(image_pairs: Iterable[Tuple[torch.Tensor, torch.Tensor]],
+                                  pipeline: DepthEstimationPipeline, hooks: Iterable = None) -> None:
+    """Frame loop of depth_estimation_pipeline_runner.py:38-66 over any iterable of (left, right) pairs.
+    Hooks are objects with on_pipeline_start() / process(context) / on_pipeline_end()."""
+    hooks = list(hooks or [])
+    config = pipeline.get_configuration()
+    for hook in hooks:
+        hook.on_pipeline_start()
+    for frame_index, (left_view, right_view) in enumerate(image_pairs):
+        if tuple(left_view.shape[-2:]) != tuple(config.image_shape):
+            raise RuntimeError(f"Incompatible image shapes between pipeline configuration and camera."
+                               f"Pipeline expects: {config.image_shape} but camera provides: {tuple(left_view.shape[-2:])}.")
+        result = pipeline.process(left_view, right_view)
+        context = DepthEstimationPipelineContext(disparity_map=result.disparity_map, left_image=result.left_image,
+                                                 right_image=result.right_image, config=config, frame_index=frame_index)
+        for hook in hooks:
+            hook.process(context)
+    for hook in hooks:
+        hook.on_pipeline_end()

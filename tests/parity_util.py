@@ -41,13 +41,16 @@ def oracle_config_from_array(O, arr):
     return O.make_config(**{f: int(v) for f, v in zip(CONFIG_FIELDS, arr)})
 
 
-def run_cuda_all_stages(left_u8, right_u8, cfg_kwargs, variant="auto", dtype="u8", volumes=True, frames_per_launch=0):
+def run_cuda_all_stages(left_u8, right_u8, cfg_kwargs, variant="auto", dtype="u8", volumes=True, frames_per_launch=0,
+                        compat=None):
     """Runs the CUDA path on one frame and returns every intermediate as numpy arrays."""
     import torch
     from stereo_depth_b200 import cuda_depth
     cfg = cuda_depth.StereoMatchingConfiguration(**cfg_kwargs)
     sm = cuda_depth.StereoMatching(cfg, frames_per_launch=frames_per_launch)
     sm.set_variant(variant)
+    if compat is not None:
+        sm.set_compat(compat)
     vols = sm.debug_volumes(True) if volumes else None
     l = torch.from_numpy(left_u8).cuda()
     r = torch.from_numpy(right_u8).cuda()

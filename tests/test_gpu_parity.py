@@ -24,9 +24,12 @@ def cfg_kw(H, W, K, mn, mx, **extra):
     return d
 
 
-def oracle_all(kw, l, r):
+def oracle_all(kw, l, r, mode=None):
     cfg = O.make_config(**kw)
-    ref = O.run(cfg, l, r, mode=O.MODE_SAFE, want=O.ALL_STAGES)
+    if mode is None:
+        # the kernels' default: SAFE padding, and the reference's absolute-index read when min_disparity/K != 0
+        mode = O.MODE_COMPAT if kw["min_disparity"] // kw["downscale_factor"] else O.MODE_SAFE
+    ref = O.run(cfg, l, r, mode=mode, want=O.ALL_STAGES)
     ref["agg3"] = agg3_from_volume(ref["agg"], ref["wta"], kw["min_disparity"] // kw["downscale_factor"])
     return ref
 
@@ -85,7 +88,9 @@ def test_matches_reference_fixtures(name, variant):
     g = load_golden(name)
     kw = {f: int(v) for f, v in zip(O.CONFIG_FIELDS, g["config"])}
     cfg = oracle_config_from_array(O, g["config"])
-    t = O.run(cfg, g["left"], g["right"], want=("taint_agg", "taint_refined", "taint_out"))
+    mode = O.MODE_COMPAT if kw["min_disparity"] // kw["downscale_factor"] else O.MODE_SAFE
+    t = O.run(cfg, g["left"], g["right"], mode=mode, want=("taint_agg", "taint_refined", "taint_out"))
+    t = {k: v & 3 for k, v in t.items()}   # bit 2 (absolute-index read) is reproduced by the default compat mode
     got = run_cuda_all_stages(g["left"], g["right"], kw, variant=variant, dtype="f32")
     for st in ("gray_l", "gray_r", "pool_l", "pool_r", "cost"):
         assert mismatch(got[st], g[st]) == 0, st
@@ -93,15 +98,12 @@ def test_matches_reference_fixtures(name, variant):
     L = g["agg"].shape[2]
     assert mismatch(got["agg"], g["agg"], np.repeat(ok_a[..., None], L, axis=2)) == 0
     assert mismatch(got["wta"], g["wta"], ok_a) == 0
-    if kw["min_disparity"] == 0:
-        assert mismatch(got["refined"], g["refined"], ok_r) == 0
-        assert mismatch(got["out"], g["out"], ok_o) == 0
-        assert mismatch(got["out"], g["out_api"], ok_o) == 0
-        assert ok_o.mean() > 0.5
-    else:
-        # documented deviation: the reference indexes the aggregated volume with the absolute
-        # disparity (secondary_matching.cu:28-31); we use the relative one.  WTA is still identical.
-        assert ok_a.mean() > 0.5
+    # min_disparity != 0 (g5_k2_mind): the default compat mode reproduces the reference's absolute-index
+    # read of the aggregated volume (secondary_matching.cu:28-31), so refined/filled outputs match too.
+    assert mismatch(got["refined"], g["refined"], ok_r) == 0
+    assert mismatch(got["out"], g["out"], ok_o) == 0
+    assert mismatch(got["out"], g["out_api"], ok_o) == 0
+    assert ok_o.mean() > 0.5
 
 
 def test_full_size_c3_vs_oracle():
@@ -251,3 +253,55 @@ def test_profile_hook_counts_launches():
     assert all(n == 3 for _, n in prof.values())        # 5 frames / 2 per launch = 3 chunks
     assert all(ms > 0 for ms, _ in prof.values())
     sm.profile(False)
+
+
+def test_pipeline_shim_matches_backend():
+    """DepthEstimationPipeline shim (depth_estimation_pipeline.py:47-87): default K=2, config plumbing, hooks."""
+    import torch
+    from stereo_depth_b200 import pipeline as P
+    H, W, D = 96, 160, 32
+    l, r, _ = make_pair(H, W, D, seed=3)
+    cfg = P.DepthEstimationPipelineConfig().update(image_shape=(H, W), min_disparity=0, max_disparity=D - 1)
+    with pytest.raises(RuntimeError, match="Unexpected keyword"):
+        cfg.update(nope=1)
+    pipe = P.DepthEstimationPipeline(cfg)
+    res = pipe.process(torch.from_numpy(l), torch.from_numpy(r))
+    ref = O.run(O.make_config(height=H, width=W, downscale_factor=2, min_disparity=0, max_disparity=D - 1), l, r)["out"]
+    assert mismatch(res.disparity_map.cpu().numpy(), ref) == 0
+    assert res.left_image.is_cuda
+    with pytest.raises(RuntimeError, match="right_image is required"):
+        pipe.process(torch.from_numpy(l))
+    with pytest.raises(RuntimeError, match="Unsupported stereo matching backend"):
+        P.DepthEstimationPipeline(P.DepthEstimationPipelineConfig(stereo_matching_backend="gwcnet"))
+
+    class Hook:
+        def __init__(self):
+            self.events = []
+
+        def on_pipeline_start(self):
+            self.events.append("start")
+
+        def process(self, ctx):
+            self.events.append(ctx.frame_index)
+
+        def on_pipeline_end(self):
+            self.events.append("end")
+
+    h = Hook()
+    P.run_depth_estimation_pipeline([(torch.from_numpy(l), torch.from_numpy(r))] * 2, pipe, [h])
+    assert h.events == ["start", 0, 1, "end"]
+
+
+@pytest.mark.parametrize("variant", ["generic", "fast"])
+def test_min_disparity_compat_switch(variant):
+    """min_disparity != 0: compat on (default) == oracle MODE_COMPAT, compat off == oracle MODE_SAFE, on every cell."""
+    H, W, K, mn, mx = 72, 136, 2, 10, 41
+    kw = cfg_kw(H, W, K, mn, mx)
+    l, r, _ = make_pair(H, W, mx + 1, seed=8)
+    on = run_cuda_all_stages(l, r, kw, variant=variant)
+    off = run_cuda_all_stages(l, r, kw, variant=variant, compat=False)
+    ref_on, ref_off = oracle_all(kw, l, r, O.MODE_COMPAT), oracle_all(kw, l, r, O.MODE_SAFE)
+    for st in STAGES:
+        assert mismatch(on[st], ref_on[st]) == 0, st
+        assert mismatch(off[st], ref_off[st]) == 0, st
+    assert mismatch(ref_on["refined"], ref_off["refined"]) > 0   # the bug is observable on this input

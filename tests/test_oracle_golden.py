@@ -16,12 +16,12 @@ def test_fixtures_present():
 
 
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("mode", [O.MODE_REF, O.MODE_SAFE])
+@pytest.mark.parametrize("mode", [O.MODE_REF, O.MODE_SAFE, O.MODE_COMPAT])
 def test_oracle_matches_reference(name, mode):
     g = load_golden(name)
     cfg = oracle_config_from_array(O, g["config"])
     res = O.run(cfg, g["left"], g["right"], mode=mode, want=O.ALL_STAGES)
-    bad = 1 if mode == O.MODE_REF else 3
+    bad = {O.MODE_REF: 1, O.MODE_COMPAT: 3, O.MODE_SAFE: 7}[mode]   # bits: 1 undefined, 2 aliased read, 4 absolute-index read (min_d != 0)
     for st in ("gray_l", "gray_r", "pool_l", "pool_r", "cost"):
         assert mismatch(res[st], g[st]) == 0, st  # defined everywhere
     ok_a = (res["taint_agg"] & bad) == 0
