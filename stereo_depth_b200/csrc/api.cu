@@ -12,7 +12,7 @@
 using namespace sd;
 
 namespace {
-constexpr int kSlots = 3;  // host pipeline depth (H2D / compute / D2H in flight)
+constexpr int kSlots = 4;  // host pipeline depth (H2D / compute / D2H in flight)
 }
 
 struct sd_handle {
@@ -353,9 +353,17 @@ int sd_compute_host(sd_handle *h, const void *left, const void *right, int dtype
     int rc = ensure_host_pipeline(h, dtype);
     if (rc != SD_OK) return rc;
     const size_t inb = in_bytes_per_frame(h, dtype), outn = (size_t)h->g.H * h->g.W;
+    // Chunk schedule: a short first chunk (its H2D copy cannot overlap anything) and a short last chunk (neither
+    // can its D2H copy); full chunks in between keep the fused kernel's wave quantisation efficient.
+    const int edge = (h->chunk >= 4 && n_frames >= 3 * h->chunk) ? 2 : h->chunk;
     int it = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += h->chunk, it++) {
-        const int nf = (n_frames - f0 < h->chunk) ? n_frames - f0 : h->chunk;
+    for (int f0 = 0; f0 < n_frames; it++) {
+        int nf = h->chunk;
+        const int left_over = n_frames - f0;
+        if (f0 == 0) nf = edge;
+        else if (left_over <= edge) nf = left_over;
+        else if (left_over - edge < h->chunk) nf = left_over - edge;
+        if (nf > left_over) nf = left_over;
         const int sl = it % kSlots;
         // inputs of slot sl may be overwritten once the kernels of its previous use are done
         if (it >= kSlots) SD_CUDA(h, cudaStreamWaitEvent(h->st_h2d, h->ev_comp[sl], 0));
@@ -371,6 +379,7 @@ int sd_compute_host(sd_handle *h, const void *left, const void *right, int dtype
         SD_CUDA(h, cudaStreamWaitEvent(h->st_d2h, h->ev_comp[sl], 0));
         SD_CUDA(h, cudaMemcpyAsync(out + outn * f0, h->dout[sl], outn * nf * sizeof(float), cudaMemcpyDeviceToHost, h->st_d2h));
         SD_CUDA(h, cudaEventRecord(h->ev_d2h[sl], h->st_d2h));
+        f0 += nf;
     }
     SD_CUDA(h, cudaStreamSynchronize(h->st_d2h));
     SD_CUDA(h, cudaStreamSynchronize(h->st_comp));

@@ -20,46 +20,60 @@
 namespace sd {
 namespace {
 
+// x / K for the compile-time factors the reference is used with (exact: K is a power of two), IEEE division otherwise.
+template <int KT>
+__device__ __forceinline__ float div_k(float x, float fk) {
+    if (KT == 1) return x;
+    if (KT == 2) return __fmul_rn(x, 0.5f);
+    if (KT == 4) return __fmul_rn(x, 0.25f);
+    return __fdiv_rn(x, fk);
+}
+
 // gl = left gray of this handle's (local) image; glg = left gray of the GLOBAL image (== gl outside band mode).
+template <int KT>
 __device__ __forceinline__ float vfill_value(const Geom &g, const float *__restrict__ gl, const float *__restrict__ glg,
                                              const float *__restrict__ disp, int r, int c) {
-    const int K = g.K, x = r / K, i = r - x * K, yd = c / K;
+    const int K = KT > 0 ? KT : g.K, x = r / K, i = r - x * K, yd = c / K;
     const float fk = (float)K;
     const float p = __fmul_rn(fk, __ldg(disp + (size_t)x * g.Wd + yd));
     const int xg = wrapm(x + g.band_x_off, g.Hd_glob);  // global pooled row (the reference's x)
     if (i == 0 || xg == 0 || x == 0) return p;
     const float n = __fmul_rn(fk, __ldg(disp + (size_t)(x - 1) * g.Wd + yd));
     if (fabsf(__fsub_rn(p, n)) <= g.threshold)
-        return __fadd_rn(p, __fdiv_rn(__fmul_rn((float)i, __fsub_rn(n, p)), fk));
+        return __fadd_rn(p, div_k<KT>(__fmul_rn((float)i, __fsub_rn(n, p)), fk));
     const float prev_color = __ldg(gl + (size_t)(K * x) * g.W + c);
     const float next_color = __ldg(glg + (size_t)wrapm((K + 1) * xg, g.H_glob) * g.W + c);
     const float cur = __ldg(gl + (size_t)r * g.W + c);
     return (fabsf(__fsub_rn(cur, prev_color)) <= fabsf(__fsub_rn(cur, next_color))) ? p : n;
 }
 
+template <int KT>
 __device__ __forceinline__ float hfill_value(const Geom &g, const float *__restrict__ gl, int r, int c, int nk,
                                              float p, float n) {
-    const int m = c - nk;
+    const int m = c - nk, K = KT > 0 ? KT : g.K;
     if (fabsf(__fsub_rn(p, n)) <= g.threshold)
-        return __fadd_rn(p, __fdiv_rn(__fmul_rn((float)m, __fsub_rn(n, p)), (float)g.K));
+        return __fadd_rn(p, div_k<KT>(__fmul_rn((float)m, __fsub_rn(n, p)), (float)K));
     const size_t o = (size_t)r * g.W;
     const float pc = __ldg(gl + o + nk);
-    const size_t cf = o + nk + g.K;
+    const size_t cf = o + nk + K;
     const float nc = (cf < (size_t)g.H * g.W) ? __ldg(gl + cf) : pc;
     const float cur = __ldg(gl + o + c);
     return (fabsf(__fsub_rn(cur, pc)) <= fabsf(__fsub_rn(cur, nc))) ? p : n;
 }
 
 // value of the "next" mod-K sample to the right of nk on row r
+template <int KT>
 __device__ __forceinline__ float next_sample(const Geom &g, const float *__restrict__ gl, const float *__restrict__ glg,
                                              const float *__restrict__ disp, int r, int nk, float p) {
-    if (nk + g.K < g.W) return vfill_value(g, gl, glg, disp, r, nk + g.K);
+    const int K = KT > 0 ? KT : g.K;
+    if (nk + K < g.W) return vfill_value<KT>(g, gl, glg, disp, r, nk + K);
     // the reference's flat index lands on column 0 of the next row -- unless this is the GLOBAL last row
-    const int rg = wrapm(r + g.band_x_off * g.K, g.H_glob);
-    if (g.W % g.K == 0 && rg + 1 < g.H_glob && r + 1 < g.H) return vfill_value(g, gl, glg, disp, r + 1, 0);
+    const int rg = wrapm(r + g.band_x_off * K, g.H_glob);
+    if (g.W % K == 0 && rg + 1 < g.H_glob && r + 1 < g.H) return vfill_value<KT>(g, gl, glg, disp, r + 1, 0);
     return p;
 }
 
+template <int KT>
 __global__ void __launch_bounds__(256) fill_kernel(Geom g, const float *__restrict__ gray, const float *__restrict__ gl_glob,
                                                    const float *__restrict__ refined, float *__restrict__ out, bool vec_ok) {
     const int c4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -78,13 +92,14 @@ __global__ void __launch_bounds__(256) fill_kernel(Geom g, const float *__restri
     for (int k = 0; k < 4; k++) {
         const int c = c4 + k;
         if (c >= g.W) break;
-        const int nk = c - c % g.K;
+        const int K = KT > 0 ? KT : g.K;
+        const int nk = c - c % K;
         if (nk != nk_cached) {
-            p = (nk_cached >= 0 && nk == nk_cached + g.K) ? n : vfill_value(g, gl, glg, disp, r, nk);
-            n = next_sample(g, gl, glg, disp, r, nk, p);
+            p = (nk_cached >= 0 && nk == nk_cached + K) ? n : vfill_value<KT>(g, gl, glg, disp, r, nk);
+            n = next_sample<KT>(g, gl, glg, disp, r, nk, p);
             nk_cached = nk;
         }
-        v[k] = hfill_value(g, gl, r, c, nk, p, n);
+        v[k] = hfill_value<KT>(g, gl, r, c, nk, p, n);
     }
     if (vec_ok && c4 + 3 < g.W) {
         *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
@@ -98,7 +113,12 @@ __global__ void __launch_bounds__(256) fill_kernel(Geom g, const float *__restri
 cudaError_t launch_fill(const Geom &g, int frames, const Scratch &s, const float *gl_glob, float *out, cudaStream_t st) {
     dim3 block(32, 8), grid(((g.W + 3) / 4 + 31) / 32, (g.H + 7) / 8, frames);
     const bool vec_ok = (g.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
-    fill_kernel<<<grid, block, 0, st>>>(g, s.gray, gl_glob, s.refined, out, vec_ok);
+    switch (g.K) {
+        case 1: fill_kernel<1><<<grid, block, 0, st>>>(g, s.gray, gl_glob, s.refined, out, vec_ok); break;
+        case 2: fill_kernel<2><<<grid, block, 0, st>>>(g, s.gray, gl_glob, s.refined, out, vec_ok); break;
+        case 4: fill_kernel<4><<<grid, block, 0, st>>>(g, s.gray, gl_glob, s.refined, out, vec_ok); break;
+        default: fill_kernel<0><<<grid, block, 0, st>>>(g, s.gray, gl_glob, s.refined, out, vec_ok); break;
+    }
     return cudaGetLastError();
 }
 
