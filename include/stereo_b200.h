@@ -140,6 +140,19 @@ int sd_frames_per_launch(sd_handle *h);
  * milliseconds and launch counts per kernel ([4] each) since the previous read, and resets them. */
 int sd_profile_enable(sd_handle *h, int on);
 int sd_profile_read(sd_handle *h, double *ms_per_kernel, int *launches_per_kernel);
+/* ---- consumers of the disparity map (stateless; device pointers; asynchronous on cuda_stream) --------------
+ * Accuracy metrics of depth_estimation_pipeline_metrics.py:18-56 over the mask `0 < gt <= max_disparity`
+ * (depth_estimation_pipeline_runner.py:85): metrics_out[4] doubles in device memory =
+ * {masked pixels, D1 outliers (|e|>3 and |e|/|gt|>0.05), pixels with |e|>threshold, sum of |e|}. */
+int sd_metrics(const float *disparity, const float *gt_disparity, long long n, float max_disparity, float threshold,
+               double *metrics_out, void *cuda_stream);
+
+/* Disparity -> depth -> point list of depth_estimation_pipeline_hooks.py:84-92 / helpers/point_cloud_helpers.py:5-13:
+ * for every pixel with disparity != invalid_disparity, in row-major order, (column, row, focal*baseline/disparity).
+ * xyz: [H*W,3] floats; scratch: ceil(H*W/1024)+1 ints, the point count is left in scratch[ceil(H*W/1024)]. */
+int sd_point_cloud(const float *disparity, int H, int W, float focal_times_baseline, float invalid_disparity, float *xyz,
+                   int *scratch, void *cuda_stream);
+
 const char *sd_last_error(sd_handle *h);
 int sd_last_cuda_error(sd_handle *h);
 

@@ -305,3 +305,33 @@ def test_min_disparity_compat_switch(variant):
         assert mismatch(on[st], ref_on[st]) == 0, st
         assert mismatch(off[st], ref_off[st]) == 0, st
     assert mismatch(ref_on["refined"], ref_off["refined"]) > 0   # the bug is observable on this input
+
+
+def test_consumers_metrics_and_point_cloud():
+    """GPU metrics / point cloud vs the reference's torch / Python formulas."""
+    import torch
+    from stereo_depth_b200 import consumers
+    rng = np.random.default_rng(1)
+    H, W = 97, 203
+    est = torch.from_numpy((rng.random((H, W)) * 70).astype(np.float32)).cuda()
+    gt = torch.from_numpy((rng.random((H, W)) * 90 - 10).astype(np.float32)).cuda()
+    max_disp = 64
+    got = consumers.evaluate(est, gt, max_disp, threshold=3.0)
+    mask = (gt <= max_disp) & (gt > 0)                                   # depth_estimation_pipeline_runner.py:85
+    e = torch.abs(est[mask] - gt[mask])
+    want_d1 = torch.mean(((e > 3) & (e / gt[mask].abs() > 0.05)).float()).item()
+    want_th = torch.mean((e > 3.0).float()).item()
+    want_mae = torch.nn.functional.l1_loss(est[mask], gt[mask]).item()
+    assert got["count"] == int(mask.sum().item())
+    assert got["D1"] == pytest.approx(want_d1, abs=1e-6)
+    assert got["Threshold_3"] == pytest.approx(want_th, abs=1e-6)
+    assert got["MAE"] == pytest.approx(want_mae, rel=1e-5)
+    # point cloud: (column, row, baseline*focal/disparity) for disparity != invalid, row-major
+    d = est.clone()
+    d[rng.random((H, W)) < 0.3] = -1.0
+    pts = consumers.point_cloud(d, focal_length=700.0, baseline=0.5, invalid_disparity=-1.0).cpu().numpy()
+    dn = d.cpu().numpy()
+    rows, cols = np.nonzero(dn != -1.0)
+    want = np.stack([cols.astype(np.float32), rows.astype(np.float32), np.float32(0.5 * 700.0) / dn[rows, cols]], axis=1)
+    assert pts.shape == want.shape
+    assert np.array_equal(pts, want)
