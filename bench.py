@@ -104,12 +104,31 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power)}
 
 
+def pin_to_gpu_numa_node(local):
+    """Run this process (and first-touch its pinned buffers) on the CPUs closest to its GPU: with one process per
+    GPU the host<->device copies of the e2e leg otherwise cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        n = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n)
+        cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:  # noqa: BLE001
+        return 0
+
+
 def dist_setup(args):
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        pin_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)

@@ -143,23 +143,31 @@ class BandedStereoMatching:
         self.H, self.W = g.height, g.width
         self._out = torch.empty((self.plan.local_rows, self.W), dtype=torch.float32, device="cuda")
         self._gray = torch.empty((self.plan.local_rows, self.W), dtype=torch.float32, device="cuda")
+        self._gl_glob = None
 
     def compute(self, left_band, right_band):
         N, p = self._N, self.plan
         for t in (left_band, right_band):
             if not t.is_cuda or tuple(t.shape) != (3, p.band_rows, self.W):
                 raise RuntimeError(f"band must be a CUDA tensor of shape [3,{p.band_rows},{self.W}], got {list(t.shape)}")
+        if left_band.dtype != right_band.dtype:
+            raise RuntimeError("left and right bands must have the same dtype")
         code = N.SD_U8 if left_band.dtype == torch.uint8 else N.SD_F32
-        # exchange step 1: raw halo rows over NVLink (ring send/recv)
-        left = exchange_halos(left_band.contiguous(), p.halo_rows, self.group)
-        right = exchange_halos(right_band.contiguous(), p.halo_rows, self.group)
+        # exchange step 1: raw halo rows of both views in ONE ring send/recv over NVLink
+        both = exchange_halos(torch.cat([left_band, right_band], dim=0), p.halo_rows, self.group)
+        left, right = both[:3], both[3:]
         stream = torch.cuda.current_stream().cuda_stream
         self.handle.set_band(0, 0, None)
         self.handle.compute_range(left.data_ptr(), right.data_ptr(), code, 1, None, stream, 0, 0)   # gray + pool
         # exchange step 2: the fill kernel's colour reference row (k+1)*x can be anywhere in the image
         self.handle.get_stage("gray_l", 0, self._gray.data_ptr(), stream)
         mine = self._gray[p.halo_rows:p.halo_rows + p.band_rows]
-        self._gl_glob = gather_rows(mine, self.rows_per_rank, self.group)
+        if self.world > 1 and len(set(self.rows_per_rank)) == 1:
+            if self._gl_glob is None:
+                self._gl_glob = torch.empty((self.H, self.W), dtype=torch.float32, device="cuda")
+            dist.all_gather_into_tensor(self._gl_glob, mine, group=self.group)
+        else:
+            self._gl_glob = gather_rows(mine, self.rows_per_rank, self.group)
         self.handle.set_band(p.pooled_row_offset, self.H, self._gl_glob.data_ptr())
         self.handle.compute_range(None, None, code, 1, self._out.data_ptr(), stream, 1, 3)
         return self._out[p.halo_rows:p.halo_rows + p.band_rows]

@@ -46,6 +46,9 @@ SEEDED = [
     (130, 150, 2, 0, 2),      # L = 2
     (66, 70, 2, 3, 3),        # L = 1
     (136, 264, 2, 0, 63),     # several tiles in both directions, tile overhang
+    (40, 48, 2, 0, 63),       # more disparity levels (32) than pooled columns (24): right view wraps repeatedly
+    (72, 600, 2, 0, 511),     # L = 256: largest shared-memory footprint of the fused kernel (1 block/SM)
+    (60, 520, 1, 0, 129),     # L = 130, K = 1
 ]
 
 
