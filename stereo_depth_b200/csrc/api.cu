@@ -123,7 +123,7 @@ int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int 
     if (k0 <= 0 && 0 <= k1) SD_CUDA(h, launch_gray_pool(h->g, left, right, dtype, frames, h->s, st));
     if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
     if (k0 <= 1 && 1 <= k1) {
-        const bool fast = (h->variant == 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g));
+        const bool fast = h->s.padl && ((h->variant == 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g)));
         // reference-compat mode materialises the aggregated volume of every frame of the chunk
         const bool all = h->s.agg_vol != nullptr;
         float *agg_out = all ? h->s.agg_vol : h->dbg_agg;
@@ -252,6 +252,11 @@ int sd_create(const sd_config *cfg, int device, int frames_per_launch, sd_handle
     SD_CUDA(h, cudaMalloc((void **)&h->s.wta4, F * nd * sizeof(float4)));
     SD_CUDA(h, cudaMalloc((void **)&h->s.edge2, F * nd * sizeof(float2)));
     SD_CUDA(h, cudaMalloc((void **)&h->s.refined, F * nd * sizeof(float)));
+    if (mbm_wta_fast_supported(g)) {
+        const PadGeom pg = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
+        SD_CUDA(h, cudaMalloc((void **)&h->s.padl, F * (size_t)pg.rows * pg.pwl * sizeof(float)));
+        SD_CUDA(h, cudaMalloc((void **)&h->s.padr, F * (size_t)pg.rows * pg.pwr * sizeof(float)));
+    }
     // The reference indexes the aggregated volume with the absolute disparity (secondary_matching.cu:28-31);
     // with min_disparity/K != 0 that differs from the relative index, so reproduce it by default.
     if (g.min_ds != 0) return sd_set_compat(h, 1);
@@ -284,6 +289,8 @@ int sd_destroy(sd_handle *h) {
         cudaFree(h->s.edge2);
         cudaFree(h->s.refined);
         cudaFree(h->s.agg_vol);
+        cudaFree(h->s.padl);
+        cudaFree(h->s.padr);
         if (h->prof_events) {
             for (cudaEvent_t e : *h->prof_events) cudaEventDestroy(e);
             delete h->prof_events;
@@ -442,7 +449,9 @@ int sd_set_variant(sd_handle *h, int variant) {
 
 int sd_launches_per_call(sd_handle *h, int n_frames) {
     if (!h || n_frames <= 0) return 0;
-    return 4 * ((n_frames + h->chunk - 1) / h->chunk);
+    // gray+pool, [pad planes for the TMA-staged specialised kernel], cost+agg+WTA, secondary, fill
+    const bool fast = h->s.padl && ((h->variant == 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g)));
+    return (fast ? 5 : 4) * ((n_frames + h->chunk - 1) / h->chunk);
 }
 
 int sd_frames_per_launch(sd_handle *h) { return h ? h->chunk : 0; }

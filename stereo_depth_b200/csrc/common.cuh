@@ -46,6 +46,31 @@ struct Geom {
     int abs_index;
 };
 
+// Wrap-padded copies of the pooled planes for the specialised fused kernel: every tile's left/right row band
+// (with the reference's circular padding, pad_index / device_functions.cuh:10-20, already applied) is a set of
+// contiguous, 16-byte aligned row segments, so the kernel stages it with TMA bulk copies (cp.async.bulk).
+//   left  plane: [rows][pwl], padded col = virtual col + 15,       padded row = virtual row + 11
+//   right plane: [rows][pwr], padded col = virtual col + shift_r   (shift_r = 10 + min_ds + Lp + a, multiple of 4)
+constexpr int kTileH = 32, kTileW = 64;   // pixels per tile of the specialised kernel
+constexpr int kBandRows = 56;             // band rows staged per tile (54 used + 2 only dead work items touch)
+constexpr int kBandLW = 96;               // left band pitch in shared memory (floats)
+struct PadGeom {
+    int tiles_x, tiles_y, rows, pwl, pwr, rw, a, shift_r;
+};
+__host__ __device__ inline PadGeom make_pad_geom(int Hd, int Wd, int L, int min_ds) {
+    PadGeom p;
+    const int Lp = (L + 1) & ~1;
+    p.tiles_x = (Wd + kTileW - 1) / kTileW;
+    p.tiles_y = (Hd + kTileH - 1) / kTileH;
+    p.rows = (p.tiles_y - 1) * kTileH + kBandRows;
+    p.a = (4 - ((10 + min_ds + Lp) & 3)) & 3;
+    p.shift_r = 10 + min_ds + Lp + p.a;
+    p.rw = (Lp + 86 + p.a + 3) & ~3;
+    p.pwl = (p.tiles_x - 1) * kTileW + kBandLW;
+    p.pwr = (p.tiles_x - 1) * kTileW + p.rw;
+    return p;
+}
+
 // Per-chunk scratch in HBM (frame-major; one chunk = frames_per_launch frames).
 //   gray  : [F][2][H][W]    float   (side 0 = left, 1 = right)
 //   pool  : [F][2][Hd][Wd]  float
@@ -59,11 +84,13 @@ struct Scratch {
     float2 *edge2;
     float *refined;
     float *agg_vol;  // [F][Hd][Wd][L] aggregated volume, only in reference-compat mode (abs_index), else NULL
+    float *padl, *padr;  // [F][rows][pwl], [F][rows][pwr] wrap-padded pooled planes (PadGeom), NULL if unsupported
 };
 
 // kernel launchers (each returns cudaGetLastError())
 cudaError_t launch_gray_pool(const Geom &g, const void *left, const void *right, int dtype, int frames,
                              const Scratch &s, cudaStream_t st);
+cudaError_t launch_pad_pooled(const Geom &g, int frames, const Scratch &s, cudaStream_t st);
 cudaError_t launch_mbm_wta_generic(const Geom &g, int frames, const Scratch &s, float *dbg_cost,
                                    float *dbg_agg, bool all_frames, cudaStream_t st);
 bool mbm_wta_fast_supported(const Geom &g);

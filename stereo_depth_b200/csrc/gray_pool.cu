@@ -145,6 +145,20 @@ __global__ void __launch_bounds__(256) gray_pool_k2_f32(const float *__restrict_
         make_float4(p[0], p[1], p[2], p[3]);
 }
 
+// Wrap-padded copies of the pooled planes (PadGeom in common.cuh).  1 thread per padded element, both views.
+__global__ void __launch_bounds__(256) pad_pooled_kernel(const float *__restrict__ pool, float *__restrict__ padl,
+                                                         float *__restrict__ padr, int Hd, int Wd, PadGeom pg) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    const int frame = blockIdx.z >> 1, side = blockIdx.z & 1;
+    const int pw = side ? pg.pwr : pg.pwl;
+    if (c >= pw) return;
+    const float *src = pool + ((size_t)frame * 2 + side) * Hd * Wd;
+    const int vr = r - 11, vc = c - (side ? pg.shift_r : 15);
+    const float v = __ldg(src + (size_t)wrapm(vr, Hd) * Wd + wrapm(vc, Wd));
+    (side ? padr : padl)[((size_t)frame * pg.rows + r) * pw + c] = v;
+}
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
@@ -170,6 +184,14 @@ cudaError_t launch_gray_pool(const Geom &g, const void *left, const void *right,
             gray_pool_generic<float><<<grid, block, 0, st>>>((const float *)left, (const float *)right, s.gray, s.pool,
                                                              g.H, g.W, g.K, g.Hd, g.Wd);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pad_pooled(const Geom &g, int frames, const Scratch &s, cudaStream_t st) {
+    const PadGeom pg = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
+    const int pw = pg.pwl > pg.pwr ? pg.pwl : pg.pwr;
+    dim3 grid((pw + 255) / 256, pg.rows, frames * 2);
+    pad_pooled_kernel<<<grid, 256, 0, st>>>(s.pool, s.padl, s.padr, g.Hd, g.Wd, pg);
     return cudaGetLastError();
 }
 

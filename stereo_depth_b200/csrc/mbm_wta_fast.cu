@@ -11,8 +11,9 @@
 //     once per window per thread and reused by every pixel of the 4x4 block whose window covers it);
 //   * the cost plane lives in shared memory with its 16-byte chunks split by parity (even chunks first,
 //     odd chunks second) so the 32-byte lane stride of the 4-pixel ownership is bank-conflict free;
-//   * the pooled left/right row bands (with the reference's circular padding already applied) are staged
-//     in shared memory once per tile and reused by all L/2 passes;
+//   * the pooled left/right row bands are staged in shared memory once per tile by TMA bulk copies
+//     (cp.async.bulk + mbarrier) from wrap-padded planes that already hold the reference's circular padding,
+//     and reused by all L/2 passes;
 //   * the 3x3 cost is computed by row-streaming 4-column strips: every |L-R| tap is evaluated once and
 //     reused by the 3 cost rows and up to 3 cost columns that contain it;
 //   * WTA keeps only (best, previous level) in registers and rewrites a pixel's 16-byte record
@@ -21,7 +22,6 @@
 // Semantics: identical to mbm_wta_generic.cu / oracle so_cost + so_aggregate + so_wta (SAFE padding).
 // References: device_functions.cuh:53-73, ncc_matching_cost_volume_construction.cu:67-76,
 // multi_block_matching_cost_aggregation.cu:56-87, wta_disparity_selection.cu:22-30.
-#include <cuda_pipeline.h>
 #include <stdlib.h>
 
 #include <type_traits>
@@ -36,7 +36,7 @@ constexpr int NCHUNK = 42;        // 16-byte chunks per cost-plane row: (BW + 20
 constexpr int HALF = 21;          // even chunks [0,21), odd chunks [21,42)
 constexpr int NSTRIP = 21;        // 4-column strips per cost-plane row
 constexpr int SEG = 9;            // cost-plane rows per cost-phase work item
-constexpr int LW = 88;            // left band row pitch (floats): 64 + 22 rounded up to 4
+constexpr int LW = kBandLW;       // left band row pitch (floats): virtual columns c0-15 .. c0+80
 
 template <int BH>
 struct Cfg {
@@ -44,17 +44,36 @@ struct Cfg {
     static constexpr int PRW = BH + 20;                        // cost-plane rows
     static constexpr int NSEG = (PRW + SEG - 1) / SEG;
     static constexpr int BR = SEG * NSEG + 2;                  // band rows (incl. rows only dead items touch)
+    static_assert(BH != kTileH || BR == kBandRows, "band geometry must match PadGeom");
     static constexpr int ITEMS = NSTRIP * NSEG;
 };
 
-__host__ __device__ inline int right_band_pitch(int L) {
-    const int Lp = (L + 1) & ~1;
-    return (Lp + 86 + 3) & ~3;
+template <int BH>
+__host__ __device__ inline size_t smem_bytes(int L, int min_ds) {
+    return (size_t)Cfg<BH>::PRW * NCHUNK * 16 + (size_t)Cfg<BH>::BR * (LW + make_pad_geom(64, 64, L, min_ds).rw) * 4;
 }
 
-template <int BH>
-__host__ __device__ inline size_t smem_bytes(int L) {
-    return (size_t)Cfg<BH>::PRW * NCHUNK * 16 + (size_t)Cfg<BH>::BR * (LW + right_band_pitch(L)) * 4;
+// ---- TMA (bulk async copy) + mbarrier helpers ---------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
 }
 
 __device__ __forceinline__ float2 lo2(const float4 &q) { return make_float2(q.x, q.y); }
@@ -78,8 +97,9 @@ __device__ __forceinline__ constexpr int chunk_pos(int q) { return (q >> 1) + (q
 
 template <int BH, bool DBG, int MODE>
 __global__ void __launch_bounds__(Cfg<BH>::NT, (BH <= 32) ? 2 : 1)
-mbm_wta_fast_kernel(Geom g, const float *__restrict__ pool, float4 *__restrict__ wta4, float2 *__restrict__ edge2,
-                    int RW, float *__restrict__ dbg_cost, float *__restrict__ dbg_agg, int all_frames) {
+mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const float *__restrict__ padr,
+                    float4 *__restrict__ wta4, float2 *__restrict__ edge2, float *__restrict__ dbg_cost,
+                    float *__restrict__ dbg_agg, int all_frames) {
     using C = Cfg<BH>;
     extern __shared__ float4 smem4[];
     float4 *plane = smem4;                                              // [PRW][42] chunks of (cell,level) pairs
@@ -91,21 +111,23 @@ mbm_wta_fast_kernel(Geom g, const float *__restrict__ pool, float4 *__restrict__
     const int Hd = g.Hd, Wd = g.Wd, L = g.L;
     const int Lp = (L + 1) & ~1, M = Lp >> 1;
     const size_t np = (size_t)Hd * Wd;
-    const float *pl = pool + (size_t)frame * 2 * np, *pr = pl + np;
+    const int RW = pg.rw;
 
-    // ---- stage the pooled row bands once per tile (circular padding applied here) ----------------
-    // cp.async (LDGSTS): every element is in flight at once instead of one exposed L2 round trip each.
-    {
-        const int warp = tid >> 5, lane = tid & 31, nwarps = C::NT / 32;
-        const int originR = c0 - 10 - g.min_ds - Lp;  // virtual column of bandR[.][0]
-        for (int rr = warp; rr < C::BR; rr += nwarps) {
-            const size_t ro = (size_t)wrapm(r0 - 11 + rr, Hd) * Wd;
-            for (int cc = lane; cc < LW; cc += 32)
-                __pipeline_memcpy_async(&bandL[rr * LW + cc], pl + ro + wrapm(c0 - 11 + cc, Wd), 4);
-            for (int cc = lane; cc < RW; cc += 32)
-                __pipeline_memcpy_async(&bandR[rr * RW + cc], pr + ro + wrapm(originR + cc, Wd), 4);
+    // ---- stage the pooled row bands once per tile with TMA bulk copies ---------------------------------
+    // The wrap-padded planes (pad_pooled_kernel) make every band row one contiguous 16-byte aligned segment:
+    // one cp.async.bulk per row and view, completion counted in bytes on an mbarrier.
+    __shared__ __align__(8) uint64_t band_bar;
+    if (tid == 0) mbar_init(&band_bar, 1);
+    __syncthreads();
+    if (tid < 32) {
+        if (tid == 0) mbar_expect_tx(&band_bar, (unsigned)(C::BR * (LW + RW) * 4));
+        __syncwarp();
+        const float *sl = padl + ((size_t)frame * pg.rows + r0) * pg.pwl + c0;
+        const float *sr = padr + ((size_t)frame * pg.rows + r0) * pg.pwr + c0;
+        for (int rr = tid; rr < C::BR; rr += 32) {
+            tma_bulk_g2s(bandL + rr * LW, sl + (size_t)rr * pg.pwl, LW * 4, &band_bar);
+            tma_bulk_g2s(bandR + rr * RW, sr + (size_t)rr * pg.pwr, (unsigned)(RW * 4), &band_bar);
         }
-        __pipeline_commit();
     }
 
     // ---- per-pixel WTA state (16 pixels, index k = a*4 + b) ---------------------------------------
@@ -128,8 +150,11 @@ mbm_wta_fast_kernel(Geom g, const float *__restrict__ pool, float4 *__restrict__
     const bool has_item = tid < C::ITEMS;
     const int strip = tid % NSTRIP, seg = tid / NSTRIP;
 
-    __pipeline_wait_prior(0);
-    __syncthreads();
+    {
+        int spins = 0;
+        while (!mbar_try_wait(&band_bar, 0))
+            if (++spins > (1 << 24)) __trap();  // a lost transaction must not hang the GPU
+    }
 
     for (int m = 0; m < M; m++) {
         const int d0 = 2 * m;
@@ -139,8 +164,8 @@ mbm_wta_fast_kernel(Geom g, const float *__restrict__ pool, float4 *__restrict__
         auto cost_phase = [&](auto aligned_tag) {
             constexpr bool ALIGNED = decltype(aligned_tag)::value;
             const int R0 = seg * SEG;
-            const float *bl = bandL + R0 * LW + strip * 4;
-            const float *br = bandR + R0 * RW + strip * 4 + (Lp - 2 - d0);
+            const float *bl = bandL + R0 * LW + strip * 4 + 4;
+            const float *br = bandR + R0 * RW + strip * 4 + (Lp - 2 - d0) + pg.a;
             float2 T[3][6];
             // Band loads are issued one full row ahead of their use through volatile asm (kept in program
             // order by the compiler): the LDS latency then overlaps the previous row's taps and chains.
@@ -206,7 +231,7 @@ mbm_wta_fast_kernel(Geom g, const float *__restrict__ pool, float4 *__restrict__
             }
         };
         if (has_item) {
-            if (((Lp - 2 - d0) & 3) == 0) cost_phase(std::true_type{});
+            if (((Lp - 2 - d0 + pg.a) & 3) == 0) cost_phase(std::true_type{});
             else cost_phase(std::false_type{});
         }
         __syncthreads();
@@ -408,13 +433,14 @@ mbm_wta_fast_kernel(Geom g, const float *__restrict__ pool, float4 *__restrict__
 template <int BH, bool DBG, int MODE>
 cudaError_t launch_t(const Geom &g, int frames, const Scratch &s, float *dbg_cost, float *dbg_agg, bool all_frames,
                      cudaStream_t st) {
-    const size_t smem = smem_bytes<BH>(g.L);
+    const size_t smem = smem_bytes<BH>(g.L, g.min_ds);
+    const PadGeom pg = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
     // per-device attribute: set on every launch (cheap) so multi-GPU processes stay correct
     cudaError_t e = cudaFuncSetAttribute(mbm_wta_fast_kernel<BH, DBG, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((g.Wd + BW - 1) / BW, (g.Hd + BH - 1) / BH, frames);
-    mbm_wta_fast_kernel<BH, DBG, MODE><<<grid, Cfg<BH>::NT, smem, st>>>(g, s.pool, s.wta4, s.edge2, right_band_pitch(g.L),
-                                                                         dbg_cost, dbg_agg, all_frames ? 1 : 0);
+    mbm_wta_fast_kernel<BH, DBG, MODE><<<grid, Cfg<BH>::NT, smem, st>>>(g, pg, s.padl, s.padr, s.wta4, s.edge2, dbg_cost,
+                                                                         dbg_agg, all_frames ? 1 : 0);
     return cudaGetLastError();
 }
 
@@ -433,12 +459,16 @@ int fast_mode() {
 }  // namespace
 
 bool mbm_wta_fast_supported(const Geom &g) {
-    return g.r_cost == 1 && g.rs == 1 && g.rm == 4 && g.rl == 10 && g.L >= 1 && smem_bytes<32>(g.L) <= 227 * 1024;
+    return g.r_cost == 1 && g.rs == 1 && g.rm == 4 && g.rl == 10 && g.L >= 1 && smem_bytes<32>(g.L, g.min_ds) <= 227 * 1024;
 }
 
 cudaError_t launch_mbm_wta_fast(const Geom &g, int frames, const Scratch &s, float *dbg_cost, float *dbg_agg,
                                 bool all_frames, cudaStream_t st) {
-    if (!mbm_wta_fast_supported(g)) return cudaErrorNotSupported;
+    if (!mbm_wta_fast_supported(g) || !s.padl || !s.padr) return cudaErrorNotSupported;
+    {
+        cudaError_t e = launch_pad_pooled(g, frames, s, st);
+        if (e != cudaSuccess) return e;
+    }
     if (dbg_cost || dbg_agg) return launch_t<32, true, 0>(g, frames, s, dbg_cost, dbg_agg, all_frames, st);
     switch (fast_mode()) {
         case 1: return launch_t<32, false, 1>(g, frames, s, dbg_cost, dbg_agg, false, st);

@@ -26,7 +26,9 @@ for kw in CASES:
     H, W, D = kw["height"], kw["width"], kw["max_disparity"] + 1
     l, r, _ = make_pair(H, W, D, seed=777)
     cfg = O.make_config(**kw)
-    ref = O.run(cfg, l, r, mode=O.MODE_SAFE, want=O.ALL_STAGES)
+    # the kernels' default semantics: SAFE padding, reference-compat absolute index when min_disparity/K != 0
+    mode = O.MODE_COMPAT if kw["min_disparity"] // kw["downscale_factor"] else O.MODE_SAFE
+    ref = O.run(cfg, l, r, mode=mode, want=O.ALL_STAGES)
     ref["agg3"] = agg3_from_volume(ref["agg"], ref["wta"], kw["min_disparity"] // kw["downscale_factor"])
     for variant in variants:
         for dtype in ("u8", "f32"):
