@@ -50,7 +50,8 @@ struct Geom {
 // (with the reference's circular padding, pad_index / device_functions.cuh:10-20, already applied) is a set of
 // contiguous, 16-byte aligned row segments, so the kernel stages it with TMA bulk copies (cp.async.bulk).
 //   left  plane: [rows][pwl], padded col = virtual col + 15,       padded row = virtual row + 11
-//   right plane: [rows][pwr], padded col = virtual col + shift_r   (shift_r = 10 + min_ds + Lp + a, multiple of 4)
+//   right plane: [rows][pwr], padded col = virtual col + shift_r   (shift_r = 10 + min_ds + Lp: a tile's band then
+//                starts at padded column c0, a multiple of 64, whatever min_ds and L are)
 constexpr int kTileH = 32, kTileW = 64;   // pixels per tile of the specialised kernel
 constexpr int kBandRows = 56;             // band rows staged per tile (54 used + 2 only dead work items touch)
 constexpr int kBandLW = 96;               // left band pitch in shared memory (floats)
@@ -63,7 +64,7 @@ __host__ __device__ inline PadGeom make_pad_geom(int Hd, int Wd, int L, int min_
     p.tiles_x = (Wd + kTileW - 1) / kTileW;
     p.tiles_y = (Hd + kTileH - 1) / kTileH;
     p.rows = (p.tiles_y - 1) * kTileH + kBandRows;
-    p.a = (4 - ((10 + min_ds + Lp) & 3)) & 3;
+    p.a = 0;  // extra left columns in the shared-memory right band (kept for layout experiments)
     p.shift_r = 10 + min_ds + Lp + p.a;
     p.rw = (Lp + 86 + p.a + 3) & ~3;
     p.pwl = (p.tiles_x - 1) * kTileW + kBandLW;
