@@ -108,11 +108,63 @@ __global__ void __launch_bounds__(256) fill_kernel(Geom g, const float *__restri
     }
 }
 
+// K = 2 fast path: a thread produces a 2-row x 4-column output block (rows 2x, 2x+1) from 3 + 3 refined
+// disparities; the rare colour-pick branches fall back to the generic helpers above, so semantics are identical.
+__global__ void __launch_bounds__(256) fill_k2_kernel(Geom g, const float *__restrict__ gray, const float *__restrict__ gl_glob,
+                                                      const float *__restrict__ refined, float *__restrict__ out) {
+    const int c4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int x = blockIdx.y * blockDim.y + threadIdx.y;
+    const int frame = blockIdx.z;
+    if (x >= g.Hd || c4 >= g.W) return;
+    const size_t plane = (size_t)g.H * g.W;
+    const float *gl = gray + (size_t)frame * 2 * plane;
+    const float *glg = gl_glob ? gl_glob : gl;
+    const float *disp = refined + (size_t)frame * g.Hd * g.Wd;
+    const int y0 = c4 >> 1;
+    const bool has3 = c4 + 4 < g.W;
+    const float *da = disp + (size_t)x * g.Wd + y0;
+    const float a0 = __ldg(da), a1 = __ldg(da + 1), a2 = has3 ? __ldg(da + 2) : 0.0f;
+    const int xg = wrapm(x + g.band_x_off, g.Hd_glob);
+    const bool first = (xg == 0) || (x == 0);  // the reference returns before the vertical fill for x == 0
+    float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f;
+    if (!first) {
+        b0 = __ldg(da - g.Wd);
+        b1 = __ldg(da - g.Wd + 1);
+        b2 = has3 ? __ldg(da - g.Wd + 2) : 0.0f;
+    }
+    const float thr = g.threshold;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int r = 2 * x + i;
+        if (r >= g.H) break;
+        auto vf = [&](float d, float dprev, int c) {
+            const float p = __fmul_rn(2.0f, d);
+            if (i == 0 || first) return p;
+            const float n = __fmul_rn(2.0f, dprev);
+            if (fabsf(__fsub_rn(p, n)) <= thr) return __fadd_rn(p, __fmul_rn(__fsub_rn(n, p), 0.5f));
+            return vfill_value<2>(g, gl, glg, disp, r, c);
+        };
+        auto hf = [&](float p, float n, int c) {
+            if (fabsf(__fsub_rn(p, n)) <= thr) return __fadd_rn(p, __fmul_rn(__fsub_rn(n, p), 0.5f));
+            return hfill_value<2>(g, gl, r, c, c - 1, p, n);
+        };
+        const float v0 = vf(a0, b0, c4), v1 = vf(a1, b1, c4 + 2);
+        const float v2 = has3 ? vf(a2, b2, c4 + 4) : next_sample<2>(g, gl, glg, disp, r, c4 + 2, v1);
+        *reinterpret_cast<float4 *>(out + (size_t)frame * plane + (size_t)r * g.W + c4) =
+            make_float4(v0, hf(v0, v1, c4 + 1), v1, hf(v1, v2, c4 + 3));
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_fill(const Geom &g, int frames, const Scratch &s, const float *gl_glob, float *out, cudaStream_t st) {
     dim3 block(32, 8), grid(((g.W + 3) / 4 + 31) / 32, (g.H + 7) / 8, frames);
     const bool vec_ok = (g.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+    if (g.K == 2 && vec_ok) {
+        dim3 grid2((g.W / 4 + 31) / 32, (g.Hd + 7) / 8, frames);
+        fill_k2_kernel<<<grid2, block, 0, st>>>(g, s.gray, gl_glob, s.refined, out);
+        return cudaGetLastError();
+    }
     switch (g.K) {
         case 1: fill_kernel<1><<<grid, block, 0, st>>>(g, s.gray, gl_glob, s.refined, out, vec_ok); break;
         case 2: fill_kernel<2><<<grid, block, 0, st>>>(g, s.gray, gl_glob, s.refined, out, vec_ok); break;

@@ -145,18 +145,29 @@ __global__ void __launch_bounds__(256) gray_pool_k2_f32(const float *__restrict_
         make_float4(p[0], p[1], p[2], p[3]);
 }
 
-// Wrap-padded copies of the pooled planes (PadGeom in common.cuh).  1 thread per padded element, both views.
+// Wrap-padded copies of the pooled planes (PadGeom in common.cuh).  A thread writes 4 consecutive padded
+// columns (STG.128) of one row of one view; the wrap is one conditional add/sub in the common case.
+__device__ __forceinline__ int wrap_near(int i, int n) {
+    if (i < 0) i += n;
+    else if (i >= n) i -= n;
+    return ((unsigned)i < (unsigned)n) ? i : wrapm(i, n);  // images narrower than the padding: true modulo
+}
+
 __global__ void __launch_bounds__(256) pad_pooled_kernel(const float *__restrict__ pool, float *__restrict__ padl,
                                                          float *__restrict__ padr, int Hd, int Wd, PadGeom pg) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int r = blockIdx.y;
     const int frame = blockIdx.z >> 1, side = blockIdx.z & 1;
-    const int pw = side ? pg.pwr : pg.pwl;
-    if (c >= pw) return;
-    const float *src = pool + ((size_t)frame * 2 + side) * Hd * Wd;
-    const int vr = r - 11, vc = c - (side ? pg.shift_r : 15);
-    const float v = __ldg(src + (size_t)wrapm(vr, Hd) * Wd + wrapm(vc, Wd));
-    (side ? padr : padl)[((size_t)frame * pg.rows + r) * pw + c] = v;
+    const int pw = side ? pg.pwr : pg.pwl;   // multiples of 4
+    if (c4 >= pw) return;
+    const float *src = pool + ((size_t)frame * 2 + side) * Hd * Wd + (size_t)wrap_near(r - 11, Hd) * Wd;
+    const int vc = c4 - (side ? pg.shift_r : 15);
+    float4 v;
+    v.x = __ldg(src + wrap_near(vc, Wd));
+    v.y = __ldg(src + wrap_near(vc + 1, Wd));
+    v.z = __ldg(src + wrap_near(vc + 2, Wd));
+    v.w = __ldg(src + wrap_near(vc + 3, Wd));
+    *reinterpret_cast<float4 *>((side ? padr : padl) + ((size_t)frame * pg.rows + r) * pw + c4) = v;
 }
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -190,7 +201,7 @@ cudaError_t launch_gray_pool(const Geom &g, const void *left, const void *right,
 cudaError_t launch_pad_pooled(const Geom &g, int frames, const Scratch &s, cudaStream_t st) {
     const PadGeom pg = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
     const int pw = pg.pwl > pg.pwr ? pg.pwl : pg.pwr;
-    dim3 grid((pw + 255) / 256, pg.rows, frames * 2);
+    dim3 grid((pw / 4 + 255) / 256, pg.rows, frames * 2);
     pad_pooled_kernel<<<grid, 256, 0, st>>>(s.pool, s.padl, s.padr, g.Hd, g.Wd, pg);
     return cudaGetLastError();
 }
