@@ -75,6 +75,13 @@ __global__ void __launch_bounds__(128) secondary_kernel(Geom g, const float *__r
             const float2 *lp = reinterpret_cast<const float2 *>(gl + (size_t)(x * K - RS) * W + (c - RS - 1));
             const float2 *rp = reinterpret_cast<const float2 *>(gr + (size_t)(x * K - RS) * W + (base - RS - KT - 1));
             const int pitch2 = W >> 1;
+            // Candidates are accumulated as packed pairs (S1,S0), (S3,S2) + scalar S4.  For even tap columns the two
+            // right-view operands of a pair are an aligned register pair straight from an LDG.64, so the tap itself is
+            // two packed ops (FADD2 with a broadcast left operand, FADD2 255-|.|); odd columns compute scalar taps
+            // into a register pair.  Either way each chain adds its taps in (row, column) order: bit-identical.
+            float2 s10 = make_float2(0.0f, 0.0f), s32 = make_float2(0.0f, 0.0f);
+            float s4 = 0.0f;
+            const float2 c255 = make_float2(255.0f, 255.0f);
 #pragma unroll 1
             for (int i = 0; i < NL; i++, lp += pitch2, rp += pitch2) {
                 float lv[NL + 1], rv[NR + 1];
@@ -91,11 +98,29 @@ __global__ void __launch_bounds__(128) secondary_kernel(Geom g, const float *__r
                     rv[2 * q + 1] = t.y;
                 }
 #pragma unroll
-                for (int j = 0; j < NL; j++)
-#pragma unroll
-                    for (int k = 0; k < NC; k++)
-                        S[k] = __fadd_rn(S[k], __fsub_rn(255.0f, fabsf(__fsub_rn(lv[j + 1], rv[j - k + 2 * KT + 1]))));
+                for (int j = 0; j < NL; j++) {
+                    const float l = lv[j + 1];
+                    if ((j & 1) == 0) {
+                        const float2 t10 = __fadd2_rn(make_float2(l, l), make_float2(-rv[j + 4], -rv[j + 5]));  // k = 1, 0
+                        const float2 t32 = __fadd2_rn(make_float2(l, l), make_float2(-rv[j + 2], -rv[j + 3]));  // k = 3, 2
+                        s10 = __fadd2_rn(s10, __fadd2_rn(c255, make_float2(-fabsf(t10.x), -fabsf(t10.y))));
+                        s32 = __fadd2_rn(s32, __fadd2_rn(c255, make_float2(-fabsf(t32.x), -fabsf(t32.y))));
+                    } else {
+                        const float u1 = __fsub_rn(255.0f, fabsf(__fsub_rn(l, rv[j + 4])));
+                        const float u0 = __fsub_rn(255.0f, fabsf(__fsub_rn(l, rv[j + 5])));
+                        const float u3 = __fsub_rn(255.0f, fabsf(__fsub_rn(l, rv[j + 2])));
+                        const float u2 = __fsub_rn(255.0f, fabsf(__fsub_rn(l, rv[j + 3])));
+                        s10 = __fadd2_rn(s10, make_float2(u1, u0));
+                        s32 = __fadd2_rn(s32, make_float2(u3, u2));
+                    }
+                    s4 = __fadd_rn(s4, __fsub_rn(255.0f, fabsf(__fsub_rn(l, rv[j + 1]))));
+                }
             }
+            S[0] = s10.y;
+            S[1 % NC] = s10.x;
+            S[2 % NC] = s32.y;
+            S[3 % NC] = s32.x;
+            S[4 % NC] = s4;
         } else if (interior) {
             const float *lp = gl + (size_t)(x * K - RS) * W + (c - RS);
             const float *rp = gr + (size_t)(x * K - RS) * W + (base - RS - KT);
