@@ -237,6 +237,17 @@ def run_ours(args):
     e2e = world * F * args.steps / e2e_s
     same = bool(torch.equal(out_h[:2], out_d[:2].cpu()))
 
+    # ---- single-frame latency through the reference-shaped call (one frame per process() call) --------
+    one_l, one_r = lh[0], rh[0]
+    for _ in range(3):
+        be.process(one_l, one_r)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        o = be.process(one_l, one_r)
+        o.cpu()
+    latency_ms = (time.perf_counter() - t0) / 20 * 1e3
+
     # ---- per-kernel device times (CUDA events inside the library, on the launching stream) ----------
     sm.profile(True)
     for _ in range(2):
@@ -270,7 +281,8 @@ def run_ours(args):
                    "parallelism": f"frame-batch x{world}, no collective"},
         "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": out_bytes, "api": "CudaStereoMatchingBackend.process_batch (sd_compute_host)",
-                "timer": "wall clock around the synchronous call, max over ranks", "matches_device_path": same},
+                "timer": "wall clock around the synchronous call, max over ranks", "matches_device_path": same,
+                "single_frame_latency_ms": round(latency_ms, 3)},
         "gpu_launches": sm.launches_per_call(F) * args.steps * world,
         "clocks": clocks,
         "roofline": {"bound": "fp32_alu", "kernel": "mbm_wta_fast_kernel (fused cost + aggregation + WTA)",
