@@ -124,14 +124,9 @@ int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int 
     if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
     if (k0 <= 1 && 1 <= k1) {
         const bool fast = h->s.padl && ((h->variant == 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g)));
-        // reference-compat mode materialises the aggregated volume of every frame of the chunk
-        const bool all = h->s.agg_vol != nullptr;
-        float *agg_out = all ? h->s.agg_vol : h->dbg_agg;
-        if (fast) SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, agg_out, all, st));
-        else SD_CUDA(h, launch_mbm_wta_generic(h->g, frames, h->s, h->dbg_cost, agg_out, all, st));
-        if (all && h->dbg_agg)
-            SD_CUDA(h, cudaMemcpyAsync(h->dbg_agg, h->s.agg_vol, (size_t)h->g.Hd * h->g.Wd * h->g.L * sizeof(float),
-                                       cudaMemcpyDeviceToDevice, st));
+        // (reference-compat mode: the kernels also materialise the aggregated volume into h->s.agg_vol)
+        if (fast) SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
+        else SD_CUDA(h, launch_mbm_wta_generic(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
     }
     if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
     if (k0 <= 2 && 2 <= k1) SD_CUDA(h, launch_secondary(h->g, frames, h->s, st));

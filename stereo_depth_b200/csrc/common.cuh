@@ -56,7 +56,7 @@ constexpr int kTileH = 32, kTileW = 64;   // pixels per tile of the specialised 
 constexpr int kBandRows = 56;             // band rows staged per tile (54 used + 2 only dead work items touch)
 constexpr int kBandLW = 96;               // left band pitch in shared memory (floats)
 struct PadGeom {
-    int tiles_x, tiles_y, rows, pwl, pwr, rw, a, shift_r;
+    int tiles_x, tiles_y, rows, pwl, pwr, rw, shift_r;
 };
 __host__ __device__ inline PadGeom make_pad_geom(int Hd, int Wd, int L, int min_ds) {
     PadGeom p;
@@ -64,9 +64,8 @@ __host__ __device__ inline PadGeom make_pad_geom(int Hd, int Wd, int L, int min_
     p.tiles_x = (Wd + kTileW - 1) / kTileW;
     p.tiles_y = (Hd + kTileH - 1) / kTileH;
     p.rows = (p.tiles_y - 1) * kTileH + kBandRows;
-    p.a = 0;  // extra left columns in the shared-memory right band (kept for layout experiments)
-    p.shift_r = 10 + min_ds + Lp + p.a;
-    p.rw = (Lp + 86 + p.a + 3) & ~3;
+    p.shift_r = 10 + min_ds + Lp;
+    p.rw = (Lp + 86 + 3) & ~3;
     p.pwl = (p.tiles_x - 1) * kTileW + kBandLW;
     p.pwr = (p.tiles_x - 1) * kTileW + p.rw;
     return p;
@@ -84,7 +83,7 @@ struct Scratch {
     float4 *wta4;
     float2 *edge2;
     float *refined;
-    float *agg_vol;  // [F][Hd][Wd][L] aggregated volume, only in reference-compat mode (abs_index), else NULL
+    float *agg_vol;  // [F][L][Hd*Wd] (plane-major) aggregated volume, only in reference-compat mode (abs_index), else NULL
     float *padl, *padr;  // [F][rows][pwl], [F][rows][pwr] wrap-padded pooled planes (PadGeom), NULL if unsupported
 };
 
@@ -93,10 +92,10 @@ cudaError_t launch_gray_pool(const Geom &g, const void *left, const void *right,
                              const Scratch &s, cudaStream_t st);
 cudaError_t launch_pad_pooled(const Geom &g, int frames, const Scratch &s, cudaStream_t st);
 cudaError_t launch_mbm_wta_generic(const Geom &g, int frames, const Scratch &s, float *dbg_cost,
-                                   float *dbg_agg, bool all_frames, cudaStream_t st);
+                                   float *dbg_agg, cudaStream_t st);
 bool mbm_wta_fast_supported(const Geom &g);
 cudaError_t launch_mbm_wta_fast(const Geom &g, int frames, const Scratch &s, float *dbg_cost,
-                                float *dbg_agg, bool all_frames, cudaStream_t st);
+                                float *dbg_agg, cudaStream_t st);
 cudaError_t launch_secondary(const Geom &g, int frames, const Scratch &s, cudaStream_t st);
 cudaError_t launch_fill(const Geom &g, int frames, const Scratch &s, const float *gl_glob, float *out, cudaStream_t st);
 

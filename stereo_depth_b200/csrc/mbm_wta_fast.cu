@@ -95,11 +95,11 @@ __device__ __forceinline__ float tap(float l, float r) { return __fsub_rn(255.0f
 // Shared-memory position (in 16 B chunks) of logical chunk q within a cost-plane row.
 __device__ __forceinline__ constexpr int chunk_pos(int q) { return (q >> 1) + (q & 1) * HALF; }
 
-template <int BH, bool DBG, int MODE>
+template <int BH, bool DBG, int MODE, bool STORE>
 __global__ void __launch_bounds__(Cfg<BH>::NT, (BH <= 32) ? 2 : 1)
 mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const float *__restrict__ padr,
                     float4 *__restrict__ wta4, float2 *__restrict__ edge2, float *__restrict__ dbg_cost,
-                    float *__restrict__ dbg_agg, int all_frames) {
+                    float *__restrict__ dbg_agg, float *__restrict__ agg_planes) {
     using C = Cfg<BH>;
     extern __shared__ float4 smem4[];
     float4 *plane = smem4;                                              // [PRW][42] chunks of (cell,level) pairs
@@ -165,7 +165,7 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
             constexpr bool ALIGNED = decltype(aligned_tag)::value;
             const int R0 = seg * SEG;
             const float *bl = bandL + R0 * LW + strip * 4 + 4;
-            const float *br = bandR + R0 * RW + strip * 4 + (Lp - 2 - d0) + pg.a;
+            const float *br = bandR + R0 * RW + strip * 4 + (Lp - 2 - d0);
             float2 T[3][6];
             // Band loads are issued one full row ahead of their use through volatile asm (kept in program
             // order by the compiler): the LDS latency then overlaps the previous row's taps and chains.
@@ -231,7 +231,7 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
             }
         };
         if (has_item) {
-            if (((Lp - 2 - d0 + pg.a) & 3) == 0) cost_phase(std::true_type{});
+            if (((Lp - 2 - d0) & 3) == 0) cost_phase(std::true_type{});
             else cost_phase(std::false_type{});
         }
         __syncthreads();
@@ -370,7 +370,7 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
         }
 
         // ================= winner-take-all update (ascending d, strict >) =============================
-        if (DBG && (frame == 0 || all_frames)) {
+        if (DBG && frame == 0) {  // debug volumes of frame 0 in the reference's [Hd][Wd][L] layout (parity tests)
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 const int x = px0 + (k >> 2), y = py0 + (k & 3);
@@ -379,13 +379,36 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
                     const float4 q = plane[R * NCHUNK + chunk_pos(s >> 1)];
                     const float2 cc = (s & 1) ? hi2(q) : lo2(q);
                     const size_t o = ((size_t)x * Wd + y) * L + d0;
-                    const size_t oa = (all_frames ? (size_t)frame * np * L : 0) + o;
-                    if (dbg_cost && frame == 0) dbg_cost[o] = cc.x;
-                    if (dbg_agg) dbg_agg[oa] = hv[k].x;
+                    if (dbg_cost) dbg_cost[o] = cc.x;
+                    if (dbg_agg) dbg_agg[o] = hv[k].x;
                     if (d0 + 1 < L) {
-                        if (dbg_cost && frame == 0) dbg_cost[o + 1] = cc.y;
-                        if (dbg_agg) dbg_agg[oa + 1] = hv[k].y;
+                        if (dbg_cost) dbg_cost[o + 1] = cc.y;
+                        if (dbg_agg) dbg_agg[o + 1] = hv[k].y;
                     }
+                }
+            }
+        }
+        if (STORE && agg_planes) {
+            // reference-compat mode: materialise the aggregated volume, plane-major [F][L][Hd*Wd] so that the 4
+            // pixels of a thread row are one coalesced 16-byte store per level
+            float *pl0 = agg_planes + ((size_t)frame * L + d0) * np + (size_t)px0 * Wd + py0;
+            const bool vec = ((Wd & 3) == 0) && (py0 + 3 < Wd);
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                if (px0 + a >= Hd) break;
+                float *q0 = pl0 + (size_t)a * Wd;
+                if (vec) {
+                    *reinterpret_cast<float4 *>(q0) = make_float4(hv[a * 4].x, hv[a * 4 + 1].x, hv[a * 4 + 2].x, hv[a * 4 + 3].x);
+                    if (d0 + 1 < L)
+                        *reinterpret_cast<float4 *>(q0 + np) =
+                            make_float4(hv[a * 4].y, hv[a * 4 + 1].y, hv[a * 4 + 2].y, hv[a * 4 + 3].y);
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 4; b++)
+                        if (py0 + b < Wd) {
+                            q0[b] = hv[a * 4 + b].x;
+                            if (d0 + 1 < L) q0[np + b] = hv[a * 4 + b].y;
+                        }
                 }
             }
         }
@@ -430,17 +453,16 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
     }
 }
 
-template <int BH, bool DBG, int MODE>
-cudaError_t launch_t(const Geom &g, int frames, const Scratch &s, float *dbg_cost, float *dbg_agg, bool all_frames,
-                     cudaStream_t st) {
+template <int BH, bool DBG, int MODE, bool STORE>
+cudaError_t launch_t(const Geom &g, int frames, const Scratch &s, float *dbg_cost, float *dbg_agg, cudaStream_t st) {
     const size_t smem = smem_bytes<BH>(g.L, g.min_ds);
     const PadGeom pg = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
     // per-device attribute: set on every launch (cheap) so multi-GPU processes stay correct
-    cudaError_t e = cudaFuncSetAttribute(mbm_wta_fast_kernel<BH, DBG, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mbm_wta_fast_kernel<BH, DBG, MODE, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((g.Wd + BW - 1) / BW, (g.Hd + BH - 1) / BH, frames);
-    mbm_wta_fast_kernel<BH, DBG, MODE><<<grid, Cfg<BH>::NT, smem, st>>>(g, pg, s.padl, s.padr, s.wta4, s.edge2, dbg_cost,
-                                                                         dbg_agg, all_frames ? 1 : 0);
+    mbm_wta_fast_kernel<BH, DBG, MODE, STORE><<<grid, Cfg<BH>::NT, smem, st>>>(g, pg, s.padl, s.padr, s.wta4, s.edge2,
+                                                                                dbg_cost, dbg_agg, s.agg_vol);
     return cudaGetLastError();
 }
 
@@ -448,10 +470,10 @@ int fast_mode() {
     static int mode = -1;
     if (mode < 0) {
         // tuning knob.  bits 0-1: V loop 0 rolled (unroll 2), 1 fully unrolled, 2 manual software pipeline;
-        // bit 2: C loop fully unrolled.
+        // (bit 2, C loop fully unrolled, spills registers and was dropped after measurement.)
         const char *e = getenv("SD_FAST_MODE");
         mode = e ? atoi(e) : 2;
-        if (mode < 0 || mode > 6 || (mode & 3) == 3) mode = 2;
+        if (mode < 0 || mode > 2) mode = 2;
     }
     return mode;
 }
@@ -463,20 +485,18 @@ bool mbm_wta_fast_supported(const Geom &g) {
 }
 
 cudaError_t launch_mbm_wta_fast(const Geom &g, int frames, const Scratch &s, float *dbg_cost, float *dbg_agg,
-                                bool all_frames, cudaStream_t st) {
+                                cudaStream_t st) {
     if (!mbm_wta_fast_supported(g) || !s.padl || !s.padr) return cudaErrorNotSupported;
     {
         cudaError_t e = launch_pad_pooled(g, frames, s, st);
         if (e != cudaSuccess) return e;
     }
-    if (dbg_cost || dbg_agg) return launch_t<32, true, 0>(g, frames, s, dbg_cost, dbg_agg, all_frames, st);
+    if (dbg_cost || dbg_agg) return launch_t<32, true, 0, true>(g, frames, s, dbg_cost, dbg_agg, st);
+    if (s.agg_vol) return launch_t<32, false, 2, true>(g, frames, s, nullptr, nullptr, st);
     switch (fast_mode()) {
-        case 1: return launch_t<32, false, 1>(g, frames, s, dbg_cost, dbg_agg, false, st);
-        case 2: return launch_t<32, false, 2>(g, frames, s, dbg_cost, dbg_agg, false, st);
-        case 4: return launch_t<32, false, 4>(g, frames, s, dbg_cost, dbg_agg, false, st);
-        case 5: return launch_t<32, false, 5>(g, frames, s, dbg_cost, dbg_agg, false, st);
-        case 6: return launch_t<32, false, 6>(g, frames, s, dbg_cost, dbg_agg, false, st);
-        default: return launch_t<32, false, 0>(g, frames, s, dbg_cost, dbg_agg, false, st);
+        case 1: return launch_t<32, false, 1, false>(g, frames, s, nullptr, nullptr, st);
+        case 2: return launch_t<32, false, 2, false>(g, frames, s, nullptr, nullptr, st);
+        default: return launch_t<32, false, 0, false>(g, frames, s, nullptr, nullptr, st);
     }
 }
 

@@ -39,7 +39,7 @@ __device__ __forceinline__ float cost_cell(const float *__restrict__ pl, const f
 __global__ void __launch_bounds__(TH *TW) mbm_wta_generic_kernel(Geom g, const float *__restrict__ pool,
                                                                   float4 *__restrict__ wta4, float2 *__restrict__ edge2,
                                                                   float *__restrict__ dbg_cost, float *__restrict__ dbg_agg,
-                                                                  int all_frames) {
+                                                                  float *__restrict__ agg_planes) {
     extern __shared__ float plane[];
     const int PR = TH + 2 * g.rl, PC = TW + 2 * g.rl;
     const int frame = blockIdx.z;
@@ -70,11 +70,12 @@ __global__ void __launch_bounds__(TH *TW) mbm_wta_generic_kernel(Geom g, const f
             for (int i = -g.rm; i <= g.rm; i++)
                 for (int j = -g.rm; j <= g.rm; j++) cs = __fadd_rn(cs, ctr[i * PC + j]);
             const float agg = __fmul_rn(__fmul_rn(hs, vs), cs);
-            if (frame == 0 || all_frames) {
+            if (frame == 0) {  // debug volumes, reference layout [Hd][Wd][L]
                 const size_t o = ((size_t)x * g.Wd + y) * g.L + d;
-                if (dbg_cost && frame == 0) dbg_cost[o] = ctr[0];
-                if (dbg_agg) dbg_agg[(all_frames ? (size_t)frame * np * g.L : 0) + o] = agg;
+                if (dbg_cost) dbg_cost[o] = ctr[0];
+                if (dbg_agg) dbg_agg[o] = agg;
             }
+            if (agg_planes) agg_planes[((size_t)frame * g.L + d) * np + (size_t)x * g.Wd + y] = agg;  // compat mode
             if (d == 0) a0 = agg;
             if (d == bd + 1) ap1 = agg;  // before bd moves: value right after the current best
             if (agg > best) {
@@ -96,14 +97,14 @@ __global__ void __launch_bounds__(TH *TW) mbm_wta_generic_kernel(Geom g, const f
 }  // namespace
 
 cudaError_t launch_mbm_wta_generic(const Geom &g, int frames, const Scratch &s, float *dbg_cost, float *dbg_agg,
-                                   bool all_frames, cudaStream_t st) {
+                                   cudaStream_t st) {
     const size_t smem = (size_t)(TH + 2 * g.rl) * (TW + 2 * g.rl) * sizeof(float);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(mbm_wta_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     dim3 grid((g.Wd + TW - 1) / TW, (g.Hd + TH - 1) / TH, frames);
-    mbm_wta_generic_kernel<<<grid, TH * TW, smem, st>>>(g, s.pool, s.wta4, s.edge2, dbg_cost, dbg_agg, all_frames ? 1 : 0);
+    mbm_wta_generic_kernel<<<grid, TH * TW, smem, st>>>(g, s.pool, s.wta4, s.edge2, dbg_cost, dbg_agg, s.agg_vol);
     return cudaGetLastError();
 }
 

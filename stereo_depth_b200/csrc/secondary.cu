@@ -219,11 +219,13 @@ __global__ void __launch_bounds__(128) secondary_kernel(Geom g, const float *__r
         if (g.abs_index && agg_vol) {
             // reference-compat: the reference reads agg[x][y][pad_index(ABSOLUTE disparity, L)] with unchecked flat
             // addressing (secondary_matching.cu:28-31): a negative pad_index lands in the previous pixel's levels.
-            const size_t fb = (size_t)frame * g.Hd * g.Wd * g.L;
+            const size_t npix = (size_t)g.Hd * g.Wd;
+            const float *vol = agg_vol + (size_t)frame * g.L * npix;   // plane-major [L][Hd*Wd]
             const long long po = ((long long)x * g.Wd + y) * g.L;
             auto rd = [&](int q, float safe) {
-                const long long flat = po + ref_pad_index(q, g.L);
-                return flat >= 0 ? __ldg(agg_vol + fb + flat) : safe;  // before the tensor: SAFE (relative) value
+                const long long flat = po + ref_pad_index(q, g.L);     // index into the reference's [Hd][Wd][L] tensor
+                if (flat < 0) return safe;                             // before the tensor: SAFE (relative) value
+                return __ldg(vol + (size_t)(flat % g.L) * npix + (size_t)(flat / g.L));
             };
             a_d = rd(dm, a_d);
             a_p1 = rd(dm + 1, a_p1);

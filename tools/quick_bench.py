@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 from stereo_depth_b200 import cuda_depth  # noqa: E402
 from stereo_depth_b200.synthetic import make_batch  # noqa: E402
 
-cases = {"C1": (480, 640, 2, 64), "C3": (1080, 1920, 2, 128), "C2": (375, 1242, 1, 128), "C5": (720, 1280, 2, 128)}
+cases = {"REFDEFAULT": (1080, 1920, 2, 263), "C4": (2160, 3840, 2, 256), "C1": (480, 640, 2, 64), "C3": (1080, 1920, 2, 128), "C2": (375, 1242, 1, 128), "C5": (720, 1280, 2, 128)}
 names = [a for a in sys.argv[1:] if a in cases] or ["C3"]
 variants = [a for a in sys.argv[1:] if a in ("generic", "fast")] or ["fast"]
 nf = 8
@@ -21,8 +21,9 @@ for name in names:
     l = torch.from_numpy(np.concatenate([l] * (nf // 2))).cuda()
     r = torch.from_numpy(np.concatenate([r] * (nf // 2))).cuda()
     for variant in variants:
+        mind = 75 if name == "REFDEFAULT" else 0   # the reference's default calibration (vmin=75, vmax=262): compat mode
         sm = cuda_depth.StereoMatching(cuda_depth.StereoMatchingConfiguration(
-            height=H, width=W, downscale_factor=K, min_disparity=0, max_disparity=D - 1), frames_per_launch=nf)
+            height=H, width=W, downscale_factor=K, min_disparity=mind, max_disparity=D - 1), frames_per_launch=nf)
         sm.set_variant(variant)
         out = sm.compute_disparity_batch(l, r)
         torch.cuda.synchronize()
