@@ -66,7 +66,11 @@ __global__ void __launch_bounds__(128) secondary_kernel(Geom g, const float *__r
         // per image row only 2r+1 left and 2r+2KT+1 right values are distinct.  RS = sad radius when it
         // is the reference default (registers), otherwise fall through to the per-tap loads below.
         constexpr int RS = 5, NL = 2 * RS + 1, NR = 2 * RS + 2 * KT + 1;
-        const int c = y * K, base = c - K * dm;
+        const int c = y * K;
+        int base = c - K * dm;
+        // Left image border: the whole right-view window [base-RS-KT-1, base+RS+KT] lies left of column 0 and wraps
+        // (circular padding) to the same columns + W -- still one contiguous, equally aligned run when W is even.
+        if (base + RS + KT < 0 && (W & 1) == 0 && base + W - RS - KT - 1 >= 0) base += W;
         const bool interior = (r == RS) && (x * K - RS >= 0) && (x * K + RS < H) && (c - RS >= 0) && (c + RS < W) &&
                               (base - RS - KT >= 0) && (base + RS + KT < W);
         if (KT == 2 && interior && (W & 1) == 0 && c - RS - 1 >= 0 && base - RS - KT - 1 >= 0) {
@@ -137,8 +141,27 @@ __global__ void __launch_bounds__(128) secondary_kernel(Geom g, const float *__r
                     for (int k = 0; k < NC; k++)
                         S[k] = __fadd_rn(S[k], __fsub_rn(255.0f, fabsf(__fsub_rn(lv[j], rv[j - k + 2 * KT]))));
             }
+        } else if (r == RS && W > K * (g.L + g.min_ds) + 4 * (RS + KT + 1) && H > 2 * RS) {
+            // border pixels: same register-blocked structure; every index is within one period of the image, so the
+            // circular padding is a single conditional add/subtract per load (no integer modulo)
+            auto near = [](int i, int n) { return i < 0 ? i + n : (i >= n ? i - n : i); };
+            const int cl = near(c - RS, W) , cr = near(near(base, W) - RS - KT, W);
+#pragma unroll 1
+            for (int i = 0; i < NL; i++) {
+                const size_t ro = (size_t)near(x * K - RS + i, H) * W;
+                float lv[NL], rv[NR];
+#pragma unroll
+                for (int j = 0; j < NL; j++) lv[j] = __ldg(gl + ro + (cl + j >= W ? cl + j - W : cl + j));
+#pragma unroll
+                for (int q = 0; q < NR; q++) rv[q] = __ldg(gr + ro + (cr + q >= W ? cr + q - W : cr + q));
+#pragma unroll
+                for (int j = 0; j < NL; j++)
+#pragma unroll
+                    for (int k = 0; k < NC; k++)
+                        S[k] = __fadd_rn(S[k], __fsub_rn(255.0f, fabsf(__fsub_rn(lv[j], rv[j - k + 2 * KT]))));
+            }
         } else if (r == RS) {
-            // border pixels: same register-blocked structure, every index wrapped (SAFE modulo padding)
+            // tiny images: true modulo on every index
 #pragma unroll 1
             for (int i = 0; i < NL; i++) {
                 const size_t ro = (size_t)wrapm(x * K - RS + i, H) * W;
