@@ -86,20 +86,32 @@ __global__ void __launch_bounds__(128) secondary_kernel(Geom g, const float *__r
             float2 s10 = make_float2(0.0f, 0.0f), s32 = make_float2(0.0f, 0.0f);
             float s4 = 0.0f;
             const float2 c255 = make_float2(255.0f, 255.0f);
+            // software pipeline: the next row's 14 loads are in flight while this row's 55 taps are evaluated
+            float2 ln[(NL + 1) / 2], rn[(NR + 1) / 2];
+#pragma unroll
+            for (int j = 0; j < (NL + 1) / 2; j++) ln[j] = __ldg(lp + j);
+#pragma unroll
+            for (int q = 0; q < (NR + 1) / 2; q++) rn[q] = __ldg(rp + q);
 #pragma unroll 1
-            for (int i = 0; i < NL; i++, lp += pitch2, rp += pitch2) {
+            for (int i = 0; i < NL; i++) {
                 float lv[NL + 1], rv[NR + 1];
 #pragma unroll
                 for (int j = 0; j < (NL + 1) / 2; j++) {
-                    const float2 t = __ldg(lp + j);
-                    lv[2 * j] = t.x;
-                    lv[2 * j + 1] = t.y;
+                    lv[2 * j] = ln[j].x;
+                    lv[2 * j + 1] = ln[j].y;
                 }
 #pragma unroll
                 for (int q = 0; q < (NR + 1) / 2; q++) {
-                    const float2 t = __ldg(rp + q);
-                    rv[2 * q] = t.x;
-                    rv[2 * q + 1] = t.y;
+                    rv[2 * q] = rn[q].x;
+                    rv[2 * q + 1] = rn[q].y;
+                }
+                if (i + 1 < NL) {
+                    lp += pitch2;
+                    rp += pitch2;
+#pragma unroll
+                    for (int j = 0; j < (NL + 1) / 2; j++) ln[j] = __ldg(lp + j);
+#pragma unroll
+                    for (int q = 0; q < (NR + 1) / 2; q++) rn[q] = __ldg(rp + q);
                 }
 #pragma unroll
                 for (int j = 0; j < NL; j++) {
