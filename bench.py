@@ -49,7 +49,7 @@ def parse_args():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--frames", type=int, default=64, help="frames per step per GPU")
     p.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
-    p.add_argument("--frames-per-launch", type=int, default=8)
+    p.add_argument("--frames-per-launch", type=int, default=0, help="0 = library default (fills whole waves of the fused kernel)")
     p.add_argument("--distinct", type=int, default=8, help="distinct synthetic frames generated (tiled to --frames)")
     p.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / reference_cuda legs")
     return p.parse_args()
@@ -256,13 +256,16 @@ def run_ours(args):
     sm.profile(False)
     b_ms, b_n = prof["cost_agg_wta"]
     frames_per_launch = sm.frames_per_launch
-    ops_per_launch = 237.0 * Hd * Wd * L * frames_per_launch           # 237 lane-ops per cell
+    # 237 lane-ops per cell; the 2 profiled passes processed 2*F frames in b_n launches (the last chunk
+    # of a pass may be shorter, so work per launch is the average)
+    ops_per_launch = 237.0 * Hd * Wd * L * (2.0 * F / b_n)
     achieved = ops_per_launch / (b_ms / b_n * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "kernelB_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(args.workload)
+            per_frame = json.load(open(tpath)).get(args.workload + "_per_frame")
+            traffic = None if per_frame is None else int(per_frame * 2.0 * F / b_n)
         except (OSError, ValueError):
             traffic = None
     kernel_ms = {k: round(v[0] / max(v[1], 1), 4) for k, v in prof.items()}
@@ -290,7 +293,8 @@ def run_ours(args):
                      "frac": round(achieved / FADD_PEAK_TOPS, 4), "traffic": traffic,
                      "peak_source": "measured fp32 add peak of the CUDA cores (128 lane-adds/clk/SM x 148 SM x 1.955 GHz, "
                                     "tools/microbench/fadd_bench; MEASURED_PEAKS.json has no ALU figure); 1 lane-op = 1 'FLOP'",
-                     "algorithmic_ops_per_launch": ops_per_launch, "launch_ms": round(b_ms / b_n, 4),
+                     "algorithmic_ops_per_launch": ops_per_launch, "frames_per_launch_avg": round(2.0 * F / b_n, 3),
+                     "launch_ms": round(b_ms / b_n, 4),
                      "share_of_step": round(b_ms / total_prof, 4), "kernel_ms_per_launch": kernel_ms},
     }
     if world == 1 and not args.no_extras:

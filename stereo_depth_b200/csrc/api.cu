@@ -227,18 +227,33 @@ int sd_create(const sd_config *cfg, int device, int frames_per_launch, sd_handle
     g.band_x_off = 0;
     g.Hd_glob = g.Hd;
     g.H_glob = g.H;
-    if (frames_per_launch <= 0) {
-        // default: keep one chunk's working set (gray+pooled+outputs) well inside the 126 MB L2
-        const size_t per_frame = (size_t)g.H * g.W * 4 * 3 + (size_t)g.Hd * g.Wd * 36;
-        frames_per_launch = (int)((48u << 20) / (per_frame ? per_frame : 1));
-        if (frames_per_launch < 1) frames_per_launch = 1;
-        if (frames_per_launch > 8) frames_per_launch = 8;
-    }
-    h->chunk = frames_per_launch;
-
     int ndev = 0;
     SD_CUDA(h, cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(h, SD_ERR_BAD_ARG, "no such CUDA device");
+    if (frames_per_launch <= 0) {
+        // Default: the chunk size (<= 16 frames, <= 2 GB of scratch) whose tile count fills whole waves of the
+        // fused kernel best -- at 2 blocks/SM a 1080p frame is 255 tiles for 296 slots, a 720p frame 120 tiles.
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        const long long tiles = (long long)((g.Wd + kTileW - 1) / kTileW) * ((g.Hd + kTileH - 1) / kTileH);
+        const PadGeom pgq = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
+        const size_t smem_b = (size_t)(kTileH + 20) * 42 * 16 + (size_t)kBandRows * (kBandLW + pgq.rw) * 4;
+        const long long slots = (long long)sms * (2 * (smem_b + 1024) <= 227 * 1024 ? 2 : 1);
+        const size_t per_frame = (size_t)g.H * g.W * 4 * 2 + (size_t)g.Hd * g.Wd * 60;
+        double best_waste = 1e30;
+        frames_per_launch = 1;
+        for (int f = 1; f <= 16; f++) {
+            if (f > 1 && (size_t)f * per_frame > ((size_t)2 << 30)) break;
+            const long long blocks = tiles * f, waves = (blocks + slots - 1) / slots;
+            const double waste = (double)(waves * slots) / (double)blocks;
+            if (waste <= best_waste + 0.005) {  // prefer larger chunks among near-equals (fewer launches)
+                if (waste < best_waste) best_waste = waste;
+                frames_per_launch = f;
+            }
+        }
+    }
+    h->chunk = frames_per_launch;
+
     DeviceGuard dg(device);
     if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
     const size_t F = h->chunk, n = (size_t)g.H * g.W, nd = (size_t)g.Hd * g.Wd;
@@ -357,14 +372,17 @@ int sd_compute_host(sd_handle *h, const void *left, const void *right, int dtype
     const size_t inb = in_bytes_per_frame(h, dtype), outn = (size_t)h->g.H * h->g.W;
     // Chunk schedule: a short first chunk (its H2D copy cannot overlap anything) and a short last chunk (neither
     // can its D2H copy); full chunks in between keep the fused kernel's wave quantisation efficient.
-    const int edge = (h->chunk >= 4 && n_frames >= 3 * h->chunk) ? 2 : h->chunk;
+    // Copies of a chunk cannot overlap its own kernels, so the host path uses chunks of at most 8 frames (the
+    // device path's larger default only matters for the fused kernel's wave quantisation).
+    const int hc = h->chunk < 8 ? h->chunk : 8;
+    const int edge = (hc >= 4 && n_frames >= 3 * hc) ? 2 : hc;
     int it = 0;
     for (int f0 = 0; f0 < n_frames; it++) {
-        int nf = h->chunk;
+        int nf = hc;
         const int left_over = n_frames - f0;
         if (f0 == 0) nf = edge;
         else if (left_over <= edge) nf = left_over;
-        else if (left_over - edge < h->chunk) nf = left_over - edge;
+        else if (left_over - edge < hc) nf = left_over - edge;
         if (nf > left_over) nf = left_over;
         const int sl = it % kSlots;
         // inputs of slot sl may be overwritten once the kernels of its previous use are done
