@@ -10,5 +10,5 @@ python bench.py --steps 2 --warmup 3 --no-extras > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-extras > gpurun_out/ncu_list.log 2>&1; echo "ncu list rc=$?"
 python tools/profile_run.py 3 > gpurun_out/plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:mbm_wta_fast -s 1 -c 1 -o gpurun_out/prof_kernelB python tools/profile_run.py 3 > gpurun_out/ncu_full.log 2>&1; echo "ncu full B rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:"gray_pool|secondary|fill_kernel|pad_pooled" -s 4 -c 4 -o gpurun_out/prof_others python tools/profile_run.py 3 > gpurun_out/ncu_full2.log 2>&1; echo "ncu full others rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:"gray_pool|secondary|fill_kernel|pad_pooled" -s 5 -c 5 -o gpurun_out/prof_others python tools/profile_run.py 3 > gpurun_out/ncu_full2.log 2>&1; echo "ncu full others rc=$?"
 fi
