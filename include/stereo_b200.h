@@ -126,7 +126,7 @@ int sd_set_debug_volumes(sd_handle *h, float *cost_volume, float *aggregated_vol
 int sd_set_compat(sd_handle *h, int on);
 
 /* Selects the fused-kernel variant: 0 = auto, 1 = generic (any radii), 2 = specialised
- * (radii 1/4/10, cost radius 1).  SD_ERR_UNSUPPORTED if the configuration does not allow it. */
+ * (radii 1/4/10, cost radius 1), 3 = warp-specialised producer/consumer schedule of the same arithmetic (experimental).  SD_ERR_UNSUPPORTED if the configuration does not allow it. */
 int sd_set_variant(sd_handle *h, int variant);
 
 /* Number of kernels one sd_compute call launches for n_frames frames. */

@@ -123,9 +123,11 @@ int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int 
     if (k0 <= 0 && 0 <= k1) SD_CUDA(h, launch_gray_pool(h->g, left, right, dtype, frames, h->s, st));
     if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
     if (k0 <= 1 && 1 <= k1) {
-        const bool fast = h->s.padl && ((h->variant == 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g)));
+        const bool fast = h->s.padl && ((h->variant >= 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g)));
         // (reference-compat mode: the kernels also materialise the aggregated volume into h->s.agg_vol)
-        if (fast) SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
+        const bool ws = h->variant == 3 && h->s.padl && !h->dbg_cost && !h->dbg_agg && mbm_wta_ws_supported(h->g);
+        if (ws) SD_CUDA(h, launch_mbm_wta_ws(h->g, frames, h->s, st));
+        else if (fast) SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
         else SD_CUDA(h, launch_mbm_wta_generic(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
     }
     if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
@@ -453,7 +455,9 @@ int sd_set_debug_volumes(sd_handle *h, float *cost_volume, float *aggregated_vol
 
 int sd_set_variant(sd_handle *h, int variant) {
     if (!h) return SD_ERR_BAD_ARG;
-    if (variant < 0 || variant > 2) return fail(h, SD_ERR_BAD_ARG, "variant must be 0, 1 or 2");
+    if (variant < 0 || variant > 3) return fail(h, SD_ERR_BAD_ARG, "variant must be 0..3");
+    if (variant == 3 && !mbm_wta_ws_supported(h->g))
+        return fail(h, SD_ERR_UNSUPPORTED, "warp-specialised fused kernel needs radii 1/4/10, cost radius 1 and L <= ~150");
     if (variant == 2 && !mbm_wta_fast_supported(h->g))
         return fail(h, SD_ERR_UNSUPPORTED, "specialised fused kernel needs radii 1/4/10, cost radius 1");
     h->variant = variant;
@@ -463,7 +467,7 @@ int sd_set_variant(sd_handle *h, int variant) {
 int sd_launches_per_call(sd_handle *h, int n_frames) {
     if (!h || n_frames <= 0) return 0;
     // gray+pool, [pad planes for the TMA-staged specialised kernel], cost+agg+WTA, secondary, fill
-    const bool fast = h->s.padl && ((h->variant == 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g)));
+    const bool fast = h->s.padl && ((h->variant >= 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g)));
     return (fast ? 5 : 4) * ((n_frames + h->chunk - 1) / h->chunk);
 }
 

@@ -64,6 +64,10 @@ __host__ __device__ inline PadGeom make_pad_geom(int Hd, int Wd, int L, int min_
     p.tiles_x = (Wd + kTileW - 1) / kTileW;
     p.tiles_y = (Hd + kTileH - 1) / kTileH;
     p.rows = (p.tiles_y - 1) * kTileH + kBandRows;
+    {   // the warp-specialised variant uses 64-row tiles and 86 band rows: allocate for whichever needs more
+        const int rows64 = ((Hd + 63) / 64 - 1) * 64 + 86;
+        if (rows64 > p.rows) p.rows = rows64;
+    }
     p.shift_r = 10 + min_ds + Lp;
     p.rw = (Lp + 86 + 3) & ~3;
     p.pwl = (p.tiles_x - 1) * kTileW + kBandLW;
@@ -96,6 +100,8 @@ cudaError_t launch_mbm_wta_generic(const Geom &g, int frames, const Scratch &s, 
 bool mbm_wta_fast_supported(const Geom &g);
 cudaError_t launch_mbm_wta_fast(const Geom &g, int frames, const Scratch &s, float *dbg_cost,
                                 float *dbg_agg, cudaStream_t st);
+bool mbm_wta_ws_supported(const Geom &g);
+cudaError_t launch_mbm_wta_ws(const Geom &g, int frames, const Scratch &s, cudaStream_t st);
 cudaError_t launch_secondary(const Geom &g, int frames, const Scratch &s, cudaStream_t st);
 cudaError_t launch_fill(const Geom &g, int frames, const Scratch &s, const float *gl_glob, float *out, cudaStream_t st);
 

@@ -159,7 +159,7 @@ class StereoMatching:
         self._handle.set_compat(on)
 
     def set_variant(self, v):
-        self._handle.set_variant({"auto": 0, "generic": 1, "fast": 2}.get(v, v))
+        self._handle.set_variant({"auto": 0, "generic": 1, "fast": 2, "ws": 3}.get(v, v))
 
     def profile(self, on=True):
         self._handle.profile_enable(on)

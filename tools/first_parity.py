@@ -34,13 +34,15 @@ for kw in CASES:
         for dtype in ("u8", "f32"):
             try:
                 t = time.time()
-                got = run_cuda_all_stages(l, r, kw, variant=variant, dtype=dtype)
+                got = run_cuda_all_stages(l, r, kw, variant=variant, dtype=dtype, volumes=(variant != "ws"))
                 dt = time.time() - t
             except Exception as e:  # noqa: BLE001
                 print(kw, variant, dtype, "FAILED:", e)
                 continue
             line = [f"{H}x{W} K={kw['downscale_factor']} d=[{kw['min_disparity']},{kw['max_disparity']}] {variant}/{dtype} ({dt:.2f}s):"]
             for st in ("gray_l", "gray_r", "pool_l", "pool_r", "cost", "agg", "wta", "agg3", "refined", "out"):
+                if st not in got:
+                    continue
                 line.append(f"{st}:{mismatch(got[st], ref[st])}/{max_abs(got[st], ref[st]):.3g}")
             print(" ".join(line), flush=True)
 print("device:", torch.cuda.get_device_name(0))

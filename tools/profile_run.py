@@ -11,14 +11,17 @@ from stereo_depth_b200 import cuda_depth  # noqa: E402
 from stereo_depth_b200.synthetic import make_batch  # noqa: E402
 import numpy as np  # noqa: E402
 
-H, W, K, D = 1080, 1920, 2, 128
+H, W, K, D = (2160, 3840, 2, 256) if os.environ.get("SD_SHAPE") == "C4" else (1080, 1920, 2, 128)
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 l, r = make_batch(2, H, W, D)
-l = torch.from_numpy(np.concatenate([l] * 4)).cuda()
-r = torch.from_numpy(np.concatenate([r] * 4)).cuda()
+nrep = 1 if H > 2000 else 4
+l = torch.from_numpy(np.concatenate([l] * nrep)).cuda()
+r = torch.from_numpy(np.concatenate([r] * nrep)).cuda()
 sm = cuda_depth.StereoMatching(cuda_depth.StereoMatchingConfiguration(height=H, width=W, downscale_factor=K,
                                                                       min_disparity=0, max_disparity=D - 1),
-                               frames_per_launch=8)
+                               frames_per_launch=2 * nrep)
+if os.environ.get("SD_VARIANT"):
+    sm.set_variant(os.environ["SD_VARIANT"])
 out = None
 for _ in range(reps):
     out = sm.compute_disparity_batch(l, r, out=out)
