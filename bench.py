@@ -279,7 +279,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {wl['name']}, {F} frames per GPU per step, frame-sharded",
                    "H": H, "W": W, "D": D, "K": K, "frames_per_gpu_per_step": F, "input": "uint8 CHW",
-                   "frames_per_launch": frames_per_launch, "distinct_frames": min(args.distinct, F),
+                   "frames_per_launch": frames_per_launch, "fused_kernel_variant": sm.active_variant, "distinct_frames": min(args.distinct, F),
                    "l2": f"inputs {in_bytes / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
                    "parallelism": f"frame-batch x{world}, no collective"},
         "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": in_bytes,
@@ -288,7 +288,7 @@ def run_ours(args):
                 "single_frame_latency_ms": round(latency_ms, 3)},
         "gpu_launches": sm.launches_per_call(F) * args.steps * world,
         "clocks": clocks,
-        "roofline": {"bound": "fp32_alu", "kernel": "mbm_wta_fast_kernel (fused cost + aggregation + WTA)",
+        "roofline": {"bound": "fp32_alu", "kernel": ("mbm_wta_ws_kernel" if sm.active_variant == "ws" else "mbm_wta_fast_kernel") + " (fused cost + aggregation + WTA)",
                      "achieved": round(achieved, 3), "peak": FADD_PEAK_TOPS, "unit": "TFLOP/s",
                      "frac": round(achieved / FADD_PEAK_TOPS, 4), "traffic": traffic,
                      "peak_source": "measured fp32 add peak of the CUDA cores (128 lane-adds/clk/SM x 148 SM x 1.955 GHz, "

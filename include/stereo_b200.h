@@ -134,6 +134,10 @@ int sd_launches_per_call(sd_handle *h, int n_frames);
 
 int sd_frames_per_launch(sd_handle *h);
 
+/* The fused-kernel variant the next sd_compute will run: 1 generic, 2 specialised, 3 warp-specialised
+ * (variant 0 = auto picks 2 or 3 per shape from a wave/tile cost model, see sd_create in api.cu). */
+int sd_active_variant(sd_handle *h);
+
 /* Per-kernel device timing for benchmarks: while enabled, sd_compute brackets each of its four
  * kernels (0 gray+pool, 1 cost+aggregation+WTA, 2 secondary matching, 3 upscale+fill) with CUDA
  * events on the launching stream.  sd_profile_read waits for the last event, returns the summed

@@ -19,7 +19,7 @@ CONFIG_FIELDS = ("height", "width", "downscale_factor", "min_disparity", "max_di
 # every symbol include/stereo_b200.h declares
 EXPORTS = ("sd_abi_version", "sd_config_default", "sd_dims", "sd_create", "sd_destroy", "sd_compute",
            "sd_compute_range", "sd_set_band", "sd_compute_host", "sd_get_stage", "sd_set_debug_volumes", "sd_set_compat", "sd_set_variant",
-           "sd_launches_per_call", "sd_frames_per_launch", "sd_profile_enable", "sd_profile_read", "sd_metrics", "sd_point_cloud",
+           "sd_launches_per_call", "sd_frames_per_launch", "sd_active_variant", "sd_profile_enable", "sd_profile_read", "sd_metrics", "sd_point_cloud",
            "sd_last_error", "sd_last_cuda_error")
 
 
@@ -64,6 +64,7 @@ def lib():
     L.sd_set_compat.argtypes = [vp, ip]
     L.sd_launches_per_call.argtypes = [vp, ip]
     L.sd_frames_per_launch.argtypes = [vp]
+    L.sd_active_variant.argtypes = [vp]
     L.sd_profile_enable.argtypes = [vp, ip]
     L.sd_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.sd_metrics.argtypes = [vp, vp, C.c_longlong, C.c_float, C.c_float, vp, vp]
@@ -149,6 +150,10 @@ class Handle:
     @property
     def frames_per_launch(self):
         return lib().sd_frames_per_launch(self._h)
+
+    @property
+    def active_variant(self):
+        return {1: "generic", 2: "fast", 3: "ws"}.get(lib().sd_active_variant(self._h), "?")
 
     def close(self):
         if self._h:

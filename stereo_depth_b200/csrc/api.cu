@@ -20,7 +20,8 @@ struct sd_handle {
     Geom g;
     int device;
     int chunk;       // frames per launch
-    int variant;     // 0 auto, 1 generic, 2 fast
+    int variant;     // 0 auto, 1 generic, 2 specialised, 3 warp-specialised
+    bool auto_ws;    // variant 0 picks the warp-specialised schedule for this shape (sd_create's cost model)
     Scratch s;
     float *dbg_cost, *dbg_agg;
     const float *gl_glob;  // band mode: left gray of the global image (device), else NULL
@@ -125,7 +126,7 @@ int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int 
     if (k0 <= 1 && 1 <= k1) {
         const bool fast = h->s.padl && ((h->variant >= 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g)));
         // (reference-compat mode: the kernels also materialise the aggregated volume into h->s.agg_vol)
-        const bool ws = h->variant == 3 && h->s.padl && !h->dbg_cost && !h->dbg_agg && mbm_wta_ws_supported(h->g);
+        const bool ws = (h->variant == 3 || (h->variant == 0 && h->auto_ws)) && h->s.padl && !h->dbg_cost && !h->dbg_agg && mbm_wta_ws_supported(h->g);
         if (ws) SD_CUDA(h, launch_mbm_wta_ws(h->g, frames, h->s, st));
         else if (fast) SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
         else SD_CUDA(h, launch_mbm_wta_generic(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
@@ -232,28 +233,40 @@ int sd_create(const sd_config *cfg, int device, int frames_per_launch, sd_handle
     int ndev = 0;
     SD_CUDA(h, cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(h, SD_ERR_BAD_ARG, "no such CUDA device");
-    if (frames_per_launch <= 0) {
-        // Default: the chunk size (<= 16 frames, <= 2 GB of scratch) whose tile count fills whole waves of the
-        // fused kernel best -- at 2 blocks/SM a 1080p frame is 255 tiles for 296 slots, a 720p frame 120 tiles.
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        const long long tiles = (long long)((g.Wd + kTileW - 1) / kTileW) * ((g.Hd + kTileH - 1) / kTileH);
-        const PadGeom pgq = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
-        const size_t smem_b = (size_t)(kTileH + 20) * 42 * 16 + (size_t)kBandRows * (kBandLW + pgq.rw) * 4;
-        const long long slots = (long long)sms * (2 * (smem_b + 1024) <= 227 * 1024 ? 2 : 1);
-        const size_t per_frame = (size_t)g.H * g.W * 4 * 2 + (size_t)g.Hd * g.Wd * 60;
-        double best_waste = 1e30;
-        frames_per_launch = 1;
+    // Cost model of the fused kernel, in SM-time per frame: a launch of F frames runs ceil(tiles*F / slots) waves;
+    // a wave costs (tiles per SM) * (tile pixels) / (measured efficiency of the variant on a full wave).
+    //   specialised kernel : 32x64 tiles, 2 per SM, 0.86     warp-specialised kernel: 64x64 tiles, 1 per SM, 0.895
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const PadGeom pgq = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
+    const size_t smem_b = (size_t)(kTileH + 20) * 42 * 16 + (size_t)kBandRows * (kBandLW + pgq.rw) * 4;
+    const int per_sm_fast = (2 * (smem_b + 1024) <= 227 * 1024) ? 2 : 1;
+    const long long tiles_x = (g.Wd + kTileW - 1) / kTileW;
+    const long long tiles_fast = tiles_x * ((g.Hd + 31) / 32), tiles_ws = tiles_x * ((g.Hd + 63) / 64);
+    const size_t per_frame = (size_t)g.H * g.W * 4 * 2 + (size_t)g.Hd * g.Wd * 60;
+    auto cost = [&](bool ws, int f) {
+        const long long slots = (long long)sms * (ws ? 1 : per_sm_fast);
+        const long long waves = ((ws ? tiles_ws : tiles_fast) * f + slots - 1) / slots;
+        const double wave = ws ? 4096.0 / 0.895 : per_sm_fast * 2048.0 / (per_sm_fast == 2 ? 0.86 : 0.80);
+        return (double)waves * wave / f;
+    };
+    const bool ws_ok = mbm_wta_fast_supported(g) && mbm_wta_ws_supported(g);
+    double best_cost = 1e300;
+    int best_f = 1;
+    bool best_ws = false;
+    for (int v = 0; v < (ws_ok ? 2 : 1); v++)
         for (int f = 1; f <= 16; f++) {
-            if (f > 1 && (size_t)f * per_frame > ((size_t)2 << 30)) break;
-            const long long blocks = tiles * f, waves = (blocks + slots - 1) / slots;
-            const double waste = (double)(waves * slots) / (double)blocks;
-            if (waste <= best_waste + 0.005) {  // prefer larger chunks among near-equals (fewer launches)
-                if (waste < best_waste) best_waste = waste;
-                frames_per_launch = f;
+            if (frames_per_launch > 0 && f != frames_per_launch) continue;
+            if (frames_per_launch <= 0 && f > 1 && (size_t)f * per_frame > ((size_t)2 << 30)) break;
+            const double c = cost(v == 1, f);
+            if (c < best_cost * 0.995 || (c <= best_cost * 1.0001 && (v == 1) == best_ws)) {  // near-ties: larger chunk
+                if (c < best_cost) best_cost = c;
+                best_f = f;
+                best_ws = (v == 1);
             }
         }
-    }
+    if (frames_per_launch <= 0) frames_per_launch = best_f;
+    h->auto_ws = best_ws;
     h->chunk = frames_per_launch;
 
     DeviceGuard dg(device);
@@ -472,6 +485,14 @@ int sd_launches_per_call(sd_handle *h, int n_frames) {
 }
 
 int sd_frames_per_launch(sd_handle *h) { return h ? h->chunk : 0; }
+
+int sd_active_variant(sd_handle *h) {
+    if (!h) return 0;
+    const bool fast = h->s.padl && ((h->variant >= 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g)));
+    const bool ws = (h->variant == 3 || (h->variant == 0 && h->auto_ws)) && h->s.padl && !h->dbg_cost && !h->dbg_agg &&
+                    mbm_wta_ws_supported(h->g);
+    return ws ? 3 : (fast ? 2 : 1);
+}
 
 int sd_profile_enable(sd_handle *h, int on) {
     if (!h) return SD_ERR_BAD_ARG;

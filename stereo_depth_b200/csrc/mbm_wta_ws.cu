@@ -36,6 +36,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
     while (!mbar_try_wait(bar, parity))
         if (++spins > (1 << 26)) __trap();  // a lost arrival must not hang the GPU
 }
+// Producers run far ahead of the consumers: back off between polls so the waiting does not eat issue slots.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, unsigned parity) {
+    int spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(400);
+        if (++spins > (1 << 22)) __trap();
+    }
+}
 
 template <bool STORE>
 __global__ void __launch_bounds__(WNT, 1)
@@ -83,7 +91,7 @@ mbm_wta_ws_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
         for (int m = 0; m < M; m++) {
             const int d0 = 2 * m, b = m & 1;
             float4 *pl = planes + b * WPLANE;
-            mbar_wait(&empty_bar[b], ((m >> 1) & 1) ^ 1);  // consumers are done with the previous contents
+            mbar_wait_relaxed(&empty_bar[b], ((m >> 1) & 1) ^ 1);  // consumers are done with the previous contents
             auto cost_phase = [&](auto aligned_tag) {
                 constexpr bool ALIGNED = decltype(aligned_tag)::value;
             const int R0 = seg * WSEG;

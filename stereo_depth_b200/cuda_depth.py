@@ -174,3 +174,7 @@ class StereoMatching:
     @property
     def frames_per_launch(self):
         return self._handle.frames_per_launch
+
+    @property
+    def active_variant(self):
+        return self._handle.active_variant

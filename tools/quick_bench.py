@@ -14,7 +14,7 @@ from stereo_depth_b200.synthetic import make_batch  # noqa: E402
 cases = {"REFDEFAULT": (1080, 1920, 2, 263), "C4": (2160, 3840, 2, 256), "C1": (480, 640, 2, 64), "C3": (1080, 1920, 2, 128), "C2": (375, 1242, 1, 128), "C5": (720, 1280, 2, 128)}
 names = [a for a in sys.argv[1:] if a in cases] or ["C3"]
 variants = [a for a in sys.argv[1:] if a in ("generic", "fast", "ws")] or ["fast"]
-nf = 8
+nf = int(os.environ.get("NF", "8"))
 for name in names:
     H, W, K, D = cases[name]
     l, r = make_batch(2, H, W, D)
