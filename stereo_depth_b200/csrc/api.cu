@@ -32,6 +32,9 @@ struct sd_handle {
     void *din_l[kSlots], *din_r[kSlots];
     float *dout[kSlots];
     cudaEvent_t ev_h2d[kSlots], ev_comp[kSlots], ev_d2h[kSlots];
+    // scratch is shared by every call on this handle: each call's stream first waits for the previous call's work
+    cudaEvent_t ev_last;
+    bool ev_last_valid;
     // optional per-kernel timing (sd_profile_enable): 5 events per chunk on the launching stream
     bool prof;
     std::vector<cudaEvent_t> *prof_events;
@@ -105,6 +108,18 @@ __global__ void extract_agg3(const float4 *__restrict__ w, const float2 *__restr
     dst[3 * i + 0] = (bd == 0) ? ed.y : v.y;
     dst[3 * i + 1] = (bd == 0) ? ed.x : v.z;
     dst[3 * i + 2] = (bd == L - 1) ? ed.x : v.w;
+}
+
+// Orders this call after the previous call on the same handle (possibly on another stream): they share scratch.
+int order_after_previous(sd_handle *h, cudaStream_t st) {
+    if (h->ev_last_valid) SD_CUDA(h, cudaStreamWaitEvent(st, h->ev_last, 0));
+    return SD_OK;
+}
+
+int mark_last_use(sd_handle *h, cudaStream_t st) {
+    SD_CUDA(h, cudaEventRecord(h->ev_last, st));
+    h->ev_last_valid = true;
+    return SD_OK;
 }
 
 int prof_mark(sd_handle *h, cudaStream_t st) {
@@ -271,6 +286,7 @@ int sd_create(const sd_config *cfg, int device, int frames_per_launch, sd_handle
 
     DeviceGuard dg(device);
     if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
+    SD_CUDA(h, cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming));
     const size_t F = h->chunk, n = (size_t)g.H * g.W, nd = (size_t)g.Hd * g.Wd;
     SD_CUDA(h, cudaMalloc((void **)&h->s.gray, F * 2 * n * sizeof(float)));
     SD_CUDA(h, cudaMalloc((void **)&h->s.pool, F * 2 * nd * sizeof(float)));
@@ -313,6 +329,7 @@ int sd_destroy(sd_handle *h) {
         cudaFree(h->s.wta4);
         cudaFree(h->s.edge2);
         cudaFree(h->s.refined);
+        if (h->ev_last) cudaEventDestroy(h->ev_last);
         cudaFree(h->s.agg_vol);
         cudaFree(h->s.padl);
         cudaFree(h->s.padr);
@@ -333,14 +350,15 @@ int sd_compute(sd_handle *h, const void *left, const void *right, int dtype, int
     DeviceGuard dg(h->device);
     if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t st = (cudaStream_t)stream;
+    int rc = order_after_previous(h, st);
+    if (rc != SD_OK) return rc;
     const size_t inb = in_bytes_per_frame(h, dtype), outn = (size_t)h->g.H * h->g.W;
     for (int f0 = 0; f0 < n_frames; f0 += h->chunk) {
         const int nf = (n_frames - f0 < h->chunk) ? n_frames - f0 : h->chunk;
-        const int rc = run_chunk(h, (const char *)left + inb * f0, (const char *)right + inb * f0, dtype, nf,
-                                 out + outn * f0, st);
+        rc = run_chunk(h, (const char *)left + inb * f0, (const char *)right + inb * f0, dtype, nf, out + outn * f0, st);
         if (rc != SD_OK) return rc;
     }
-    return SD_OK;
+    return mark_last_use(h, st);
 }
 
 int sd_compute_range(sd_handle *h, const void *left, const void *right, int dtype, int n_frames, float *out,
@@ -353,7 +371,11 @@ int sd_compute_range(sd_handle *h, const void *left, const void *right, int dtyp
     if (n_frames <= 0 || n_frames > h->chunk) return fail(h, SD_ERR_SHAPE, "sd_compute_range handles at most frames_per_launch frames");
     DeviceGuard dg(h->device);
     if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
-    return run_chunk(h, left, right, dtype, n_frames, out, (cudaStream_t)stream, first_kernel, last_kernel);
+    int rc = order_after_previous(h, (cudaStream_t)stream);
+    if (rc != SD_OK) return rc;
+    rc = run_chunk(h, left, right, dtype, n_frames, out, (cudaStream_t)stream, first_kernel, last_kernel);
+    if (rc != SD_OK) return rc;
+    return mark_last_use(h, (cudaStream_t)stream);
 }
 
 int sd_set_band(sd_handle *h, int pooled_row_offset, int global_height, const float *global_left_gray) {
@@ -383,6 +405,8 @@ int sd_compute_host(sd_handle *h, const void *left, const void *right, int dtype
     DeviceGuard dg(h->device);
     if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
     int rc = ensure_host_pipeline(h, dtype);
+    if (rc != SD_OK) return rc;
+    rc = order_after_previous(h, h->st_comp);
     if (rc != SD_OK) return rc;
     const size_t inb = in_bytes_per_frame(h, dtype), outn = (size_t)h->g.H * h->g.W;
     // Chunk schedule: a short first chunk (its H2D copy cannot overlap anything) and a short last chunk (neither
@@ -418,6 +442,7 @@ int sd_compute_host(sd_handle *h, const void *left, const void *right, int dtype
     }
     SD_CUDA(h, cudaStreamSynchronize(h->st_d2h));
     SD_CUDA(h, cudaStreamSynchronize(h->st_comp));
+    h->ev_last_valid = false;  // everything on this handle has completed
     return SD_OK;
 }
 
@@ -428,6 +453,10 @@ int sd_get_stage(sd_handle *h, int stage, int frame, float *dst, void *stream) {
     DeviceGuard dg(h->device);
     if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        const int rc = order_after_previous(h, st);
+        if (rc != SD_OK) return rc;
+    }
     const Geom &g = h->g;
     const size_t n = (size_t)g.H * g.W, nd = (size_t)g.Hd * g.Wd;
     const int threads = 256, blocks = (int)((nd + threads - 1) / threads);

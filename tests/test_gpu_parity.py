@@ -344,3 +344,29 @@ def test_consumers_metrics_and_point_cloud():
     want = np.stack([cols.astype(np.float32), rows.astype(np.float32), np.float32(0.5 * 700.0) / dn[rows, cols]], axis=1)
     assert pts.shape == want.shape
     assert np.array_equal(pts, want)
+
+
+def test_calls_on_one_handle_are_ordered_across_streams():
+    """All calls on a handle share scratch memory: the library orders them even when they are issued on different
+    streams (or mix the asynchronous device path with the host path) without any synchronisation by the caller."""
+    import torch
+    from stereo_depth_b200 import cuda_depth
+    from stereo_depth_b200.synthetic import make_batch
+    H, W, D, n = 96, 160, 32, 6
+    L, R = make_batch(n, H, W, D, seed=17)
+    sm = cuda_depth.StereoMatching(cuda_depth.StereoMatchingConfiguration(height=H, width=W, min_disparity=0,
+                                                                          max_disparity=D - 1), frames_per_launch=2)
+    Ld, Rd = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+    want = sm.compute_disparity_batch(Ld, Rd).cpu()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            a = sm.compute_disparity_batch(Ld, Rd)
+        with torch.cuda.stream(s2):
+            b = sm.compute_disparity_batch(Ld.flip(0).contiguous(), Rd.flip(0).contiguous())
+        host = sm.compute_disparity_host(torch.from_numpy(L).pin_memory(), torch.from_numpy(R).pin_memory())
+        torch.cuda.synchronize()
+        assert torch.equal(a.cpu(), want)
+        assert torch.equal(b.cpu().flip(0), want)
+        assert torch.equal(host, want)
