@@ -370,3 +370,34 @@ def test_calls_on_one_handle_are_ordered_across_streams():
         assert torch.equal(a.cpu(), want)
         assert torch.equal(b.cpu().flip(0), want)
         assert torch.equal(host, want)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_fuzz_float_inputs_all_variants(seed):
+    """Arbitrary float32 images (fractional, negative, > 255, exact ties through repeated columns): every schedule of the
+    fused kernel must agree with the oracle bit for bit."""
+    import torch
+    from stereo_depth_b200 import cuda_depth
+    rng = np.random.default_rng(1000 + seed)
+    K = int(rng.choice([1, 2, 2, 3]))
+    Hd, Wd = int(rng.integers(20, 70)), int(rng.integers(40, 150))
+    H, W = Hd * K - int(rng.integers(0, K)), Wd * K - int(rng.integers(0, K))
+    L = int(rng.integers(1, 40))
+    mn = int(rng.integers(0, 3)) * K
+    mx = mn + (L - 1) * K + int(rng.integers(0, K))
+    kw = cfg_kw(H, W, K, mn, mx)
+    left = (rng.random((3, H, W)) * 350 - 50).astype(np.float32)
+    right = np.roll(left, -int(rng.integers(0, 2 * L + 1)), axis=2) + (rng.random((3, H, W)) < 0.3) * rng.normal(0, 4, (3, H, W))
+    right = right.astype(np.float32)
+    left[:, :, W // 2: W // 2 + 8] = left[:, :, W // 2: W // 2 + 1]          # flat stripe: exact ties
+    right[:, H // 3: H // 3 + 4] = 0.0
+    mode = O.MODE_COMPAT if mn // K else O.MODE_SAFE
+    ref = O.run(O.make_config(**kw), left, right, mode=mode, want=("pool_l", "wta", "refined", "out"))
+    lt, rt = torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda()
+    for variant in ("generic", "fast", "ws"):
+        sm = cuda_depth.StereoMatching(cuda_depth.StereoMatchingConfiguration(**kw))
+        sm.set_variant(variant)
+        out = sm.compute_disparity_map(lt, rt).cpu().numpy()
+        for st, got in (("pool_l", sm.stage("pool_l").cpu().numpy()), ("wta", sm.stage("wta").cpu().numpy()),
+                        ("refined", sm.stage("refined").cpu().numpy()), ("out", out)):
+            assert mismatch(got, ref[st]) == 0, (variant, st, kw)
