@@ -86,52 +86,53 @@ __global__ void __launch_bounds__(128) secondary_kernel(Geom g, const float *__r
             float2 s10 = make_float2(0.0f, 0.0f), s32 = make_float2(0.0f, 0.0f);
             float s4 = 0.0f;
             const float2 c255 = make_float2(255.0f, 255.0f);
-            // software pipeline: the next row's 14 loads are in flight while this row's 55 taps are evaluated
-            float2 ln[(NL + 1) / 2], rn[(NR + 1) / 2];
+            // Software pipeline with two register sets (no copies): while the 55 taps of one image row are evaluated
+            // from set A, the 14 loads of the next row are in flight into set B, and vice versa.
+            struct Row {
+                float2 l[(NL + 1) / 2], r[(NR + 1) / 2];
+            };
+            auto load_row = [&](Row &w) {
 #pragma unroll
-            for (int j = 0; j < (NL + 1) / 2; j++) ln[j] = __ldg(lp + j);
+                for (int j = 0; j < (NL + 1) / 2; j++) w.l[j] = __ldg(lp + j);
 #pragma unroll
-            for (int q = 0; q < (NR + 1) / 2; q++) rn[q] = __ldg(rp + q);
-#pragma unroll 1
-            for (int i = 0; i < NL; i++) {
-                float lv[NL + 1], rv[NR + 1];
-#pragma unroll
-                for (int j = 0; j < (NL + 1) / 2; j++) {
-                    lv[2 * j] = ln[j].x;
-                    lv[2 * j + 1] = ln[j].y;
-                }
-#pragma unroll
-                for (int q = 0; q < (NR + 1) / 2; q++) {
-                    rv[2 * q] = rn[q].x;
-                    rv[2 * q + 1] = rn[q].y;
-                }
-                if (i + 1 < NL) {
-                    lp += pitch2;
-                    rp += pitch2;
-#pragma unroll
-                    for (int j = 0; j < (NL + 1) / 2; j++) ln[j] = __ldg(lp + j);
-#pragma unroll
-                    for (int q = 0; q < (NR + 1) / 2; q++) rn[q] = __ldg(rp + q);
-                }
+                for (int q = 0; q < (NR + 1) / 2; q++) w.r[q] = __ldg(rp + q);
+                lp += pitch2;
+                rp += pitch2;
+            };
+            auto eval_row = [&](const Row &w) {
+                // lv(k) / rv(k): element k of the 12 left / 16 right values of this row
+                auto lv = [&](int k) { return (k & 1) ? w.l[k >> 1].y : w.l[k >> 1].x; };
+                auto rv = [&](int k) { return (k & 1) ? w.r[k >> 1].y : w.r[k >> 1].x; };
 #pragma unroll
                 for (int j = 0; j < NL; j++) {
-                    const float l = lv[j + 1];
+                    const float l = lv(j + 1);
                     if ((j & 1) == 0) {
-                        const float2 t10 = __fadd2_rn(make_float2(l, l), make_float2(-rv[j + 4], -rv[j + 5]));  // k = 1, 0
-                        const float2 t32 = __fadd2_rn(make_float2(l, l), make_float2(-rv[j + 2], -rv[j + 3]));  // k = 3, 2
+                        const float2 t10 = __fadd2_rn(make_float2(l, l), make_float2(-rv(j + 4), -rv(j + 5)));  // k = 1, 0
+                        const float2 t32 = __fadd2_rn(make_float2(l, l), make_float2(-rv(j + 2), -rv(j + 3)));  // k = 3, 2
                         s10 = __fadd2_rn(s10, __fadd2_rn(c255, make_float2(-fabsf(t10.x), -fabsf(t10.y))));
                         s32 = __fadd2_rn(s32, __fadd2_rn(c255, make_float2(-fabsf(t32.x), -fabsf(t32.y))));
                     } else {
-                        const float u1 = __fsub_rn(255.0f, fabsf(__fsub_rn(l, rv[j + 4])));
-                        const float u0 = __fsub_rn(255.0f, fabsf(__fsub_rn(l, rv[j + 5])));
-                        const float u3 = __fsub_rn(255.0f, fabsf(__fsub_rn(l, rv[j + 2])));
-                        const float u2 = __fsub_rn(255.0f, fabsf(__fsub_rn(l, rv[j + 3])));
+                        const float u1 = __fsub_rn(255.0f, fabsf(__fsub_rn(l, rv(j + 4))));
+                        const float u0 = __fsub_rn(255.0f, fabsf(__fsub_rn(l, rv(j + 5))));
+                        const float u3 = __fsub_rn(255.0f, fabsf(__fsub_rn(l, rv(j + 2))));
+                        const float u2 = __fsub_rn(255.0f, fabsf(__fsub_rn(l, rv(j + 3))));
                         s10 = __fadd2_rn(s10, make_float2(u1, u0));
                         s32 = __fadd2_rn(s32, make_float2(u3, u2));
                     }
-                    s4 = __fadd_rn(s4, __fsub_rn(255.0f, fabsf(__fsub_rn(l, rv[j + 1]))));
+                    s4 = __fadd_rn(s4, __fsub_rn(255.0f, fabsf(__fsub_rn(l, rv(j + 1)))));
                 }
+            };
+            static_assert(NL % 2 == 1, "row loop below assumes an odd number of rows");
+            Row ra, rb;
+            load_row(ra);
+#pragma unroll 1
+            for (int i = 0; i < NL / 2; i++) {
+                load_row(rb);
+                eval_row(ra);
+                load_row(ra);
+                eval_row(rb);
             }
+            eval_row(ra);
             S[0] = s10.y;
             S[1 % NC] = s10.x;
             S[2 % NC] = s32.y;
