@@ -129,6 +129,17 @@ int sd_set_compat(sd_handle *h, int on);
  * (radii 1/4/10, cost radius 1), 3 = warp-specialised producer/consumer schedule of the same arithmetic (experimental).  SD_ERR_UNSUPPORTED if the configuration does not allow it. */
 int sd_set_variant(sd_handle *h, int variant);
 
+/* Certified level screen in front of the specialised fused kernel (default: on wherever it is supported, i.e.
+ * variant 0/2, radii 1/4/10, 3 <= L <= 128, no debug volumes, no reference-compat volume).  A cheap kernel bounds
+ * every aggregated cost from separable sums and flags, per 32x64 tile, the level pairs that can still hold the
+ * reference's arg-max (rigorous fp32 error bound, stereo_depth_b200/csrc/mbm_screen.cu); the fused kernel then
+ * evaluates the reference's sequential chains (multi_block_matching_cost_aggregation.cu:56-87) only for those.
+ * Results are bit-identical with the screen on or off; only the run time changes (and becomes scene dependent).
+ * sd_screen_stats: fraction of level pairs the fused kernel had to evaluate since the last reset (synchronises). */
+int sd_set_screen(sd_handle *h, int on);
+int sd_screen_active(sd_handle *h);
+int sd_screen_stats(sd_handle *h, double *evaluated_fraction, int reset);
+
 /* Number of kernels one sd_compute call launches for n_frames frames. */
 int sd_launches_per_call(sd_handle *h, int n_frames);
 

@@ -19,7 +19,7 @@ CONFIG_FIELDS = ("height", "width", "downscale_factor", "min_disparity", "max_di
 # every symbol include/stereo_b200.h declares
 EXPORTS = ("sd_abi_version", "sd_config_default", "sd_dims", "sd_create", "sd_destroy", "sd_compute",
            "sd_compute_range", "sd_set_band", "sd_compute_host", "sd_get_stage", "sd_set_debug_volumes", "sd_set_compat", "sd_set_variant",
-           "sd_launches_per_call", "sd_frames_per_launch", "sd_active_variant", "sd_profile_enable", "sd_profile_read", "sd_metrics", "sd_point_cloud",
+           "sd_launches_per_call", "sd_frames_per_launch", "sd_active_variant", "sd_set_screen", "sd_screen_active", "sd_screen_stats", "sd_profile_enable", "sd_profile_read", "sd_metrics", "sd_point_cloud",
            "sd_last_error", "sd_last_cuda_error")
 
 
@@ -65,6 +65,9 @@ def lib():
     L.sd_launches_per_call.argtypes = [vp, ip]
     L.sd_frames_per_launch.argtypes = [vp]
     L.sd_active_variant.argtypes = [vp]
+    L.sd_set_screen.argtypes = [vp, ip]
+    L.sd_screen_active.argtypes = [vp]
+    L.sd_screen_stats.argtypes = [vp, C.POINTER(C.c_double), ip]
     L.sd_profile_enable.argtypes = [vp, ip]
     L.sd_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.sd_metrics.argtypes = [vp, vp, C.c_longlong, C.c_float, C.c_float, vp, vp]
@@ -134,6 +137,19 @@ class Handle:
 
     def set_variant(self, v):
         self.check(lib().sd_set_variant(self._h, v))
+
+    def set_screen(self, on):
+        self.check(lib().sd_set_screen(self._h, 1 if on else 0))
+
+    @property
+    def screen_active(self):
+        return bool(lib().sd_screen_active(self._h))
+
+    def screen_stats(self, reset=True):
+        """Fraction of level pairs the fused kernel evaluated since the last reset (1.0 without the screen)."""
+        f = C.c_double(1.0)
+        self.check(lib().sd_screen_stats(self._h, C.byref(f), 1 if reset else 0))
+        return f.value
 
     def launches_per_call(self, n_frames):
         return lib().sd_launches_per_call(self._h, n_frames)

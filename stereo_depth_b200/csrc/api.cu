@@ -22,6 +22,8 @@ struct sd_handle {
     int chunk;       // frames per launch
     int variant;     // 0 auto, 1 generic, 2 specialised, 3 warp-specialised
     bool auto_ws;    // variant 0 picks the warp-specialised schedule for this shape (sd_create's cost model)
+    bool screen;     // certified level screen in front of the specialised kernel (default on where supported)
+    int epoch;       // chunk counter, tags the out-of-range flag of the screen
     Scratch s;
     float *dbg_cost, *dbg_agg;
     const float *gl_glob;  // band mode: left gray of the global image (device), else NULL
@@ -131,6 +133,21 @@ int prof_mark(sd_handle *h, cudaStream_t st) {
     return SD_OK;
 }
 
+// The level screen runs in front of the specialised kernel only: not in the debug / reference-compat modes (they need
+// every level of the volume) and not with an explicitly selected generic or warp-specialised variant.
+bool screen_active(const sd_handle *h) {
+    return h->screen && h->s.pass_mask && h->s.padl && (h->variant == 0 || h->variant == 2) && !h->dbg_cost &&
+           !h->dbg_agg && !h->s.agg_vol && mbm_screen_supported(h->g);
+}
+
+// 1 generic, 2 specialised, 3 warp-specialised
+int active_variant(const sd_handle *h) {
+    const bool fast = h->s.padl && ((h->variant >= 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g)));
+    const bool ws = (h->variant == 3 || (h->variant == 0 && h->auto_ws && !screen_active(h))) && h->s.padl &&
+                    !h->dbg_cost && !h->dbg_agg && mbm_wta_ws_supported(h->g);
+    return ws ? 3 : (fast ? 2 : 1);
+}
+
 int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int frames, float *out, cudaStream_t st,
               int k0 = 0, int k1 = 3) {
     int rc;
@@ -139,11 +156,11 @@ int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int 
     if (k0 <= 0 && 0 <= k1) SD_CUDA(h, launch_gray_pool(h->g, left, right, dtype, frames, h->s, st));
     if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
     if (k0 <= 1 && 1 <= k1) {
-        const bool fast = h->s.padl && ((h->variant >= 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g)));
         // (reference-compat mode: the kernels also materialise the aggregated volume into h->s.agg_vol)
-        const bool ws = (h->variant == 3 || (h->variant == 0 && h->auto_ws)) && h->s.padl && !h->dbg_cost && !h->dbg_agg && mbm_wta_ws_supported(h->g);
-        if (ws) SD_CUDA(h, launch_mbm_wta_ws(h->g, frames, h->s, st));
-        else if (fast) SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
+        h->s.range_epoch = ++h->epoch;
+        const int v = active_variant(h);
+        if (v == 3) SD_CUDA(h, launch_mbm_wta_ws(h->g, frames, h->s, st));
+        else if (v == 2) SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st, screen_active(h)));
         else SD_CUDA(h, launch_mbm_wta_generic(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
     }
     if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
@@ -297,6 +314,16 @@ int sd_create(const sd_config *cfg, int device, int frames_per_launch, sd_handle
         const PadGeom pg = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
         SD_CUDA(h, cudaMalloc((void **)&h->s.padl, F * (size_t)pg.rows * pg.pwl * sizeof(float)));
         SD_CUDA(h, cudaMalloc((void **)&h->s.padr, F * (size_t)pg.rows * pg.pwr * sizeof(float)));
+        SD_CUDA(h, cudaMalloc((void **)&h->s.range_flag, sizeof(int)));
+        SD_CUDA(h, cudaMemset(h->s.range_flag, 0, sizeof(int)));
+        if (mbm_screen_supported(g)) {
+            SD_CUDA(h, cudaMalloc((void **)&h->s.pass_mask, F * (size_t)pg.tiles_x * pg.tiles_y * 4 * sizeof(unsigned)));
+            SD_CUDA(h, cudaMalloc((void **)&h->s.tile_order, F * (size_t)pg.tiles_x * pg.tiles_y * kScreenBuckets * sizeof(int)));
+            SD_CUDA(h, cudaMalloc((void **)&h->s.bucket_count, kScreenBuckets * sizeof(int)));
+            SD_CUDA(h, cudaMalloc((void **)&h->s.screen_stats, 2 * sizeof(unsigned long long)));
+            SD_CUDA(h, cudaMemset(h->s.screen_stats, 0, 2 * sizeof(unsigned long long)));
+            h->screen = true;
+        }
     }
     // The reference indexes the aggregated volume with the absolute disparity (secondary_matching.cu:28-31);
     // with min_disparity/K != 0 that differs from the relative index, so reproduce it by default.
@@ -333,6 +360,11 @@ int sd_destroy(sd_handle *h) {
         cudaFree(h->s.agg_vol);
         cudaFree(h->s.padl);
         cudaFree(h->s.padr);
+        cudaFree(h->s.pass_mask);
+        cudaFree(h->s.tile_order);
+        cudaFree(h->s.bucket_count);
+        cudaFree(h->s.screen_stats);
+        cudaFree(h->s.range_flag);
         if (h->prof_events) {
             for (cudaEvent_t e : *h->prof_events) cudaEventDestroy(e);
             delete h->prof_events;
@@ -508,19 +540,37 @@ int sd_set_variant(sd_handle *h, int variant) {
 
 int sd_launches_per_call(sd_handle *h, int n_frames) {
     if (!h || n_frames <= 0) return 0;
-    // gray+pool, [pad planes for the TMA-staged specialised kernel], cost+agg+WTA, secondary, fill
-    const bool fast = h->s.padl && ((h->variant >= 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g)));
-    return (fast ? 5 : 4) * ((n_frames + h->chunk - 1) / h->chunk);
+    // gray+pool, [pad planes for the TMA-staged specialised kernels], [level screen], cost+agg+WTA, secondary, fill
+    const int per_chunk = 4 + (active_variant(h) >= 2 ? 1 : 0) + (active_variant(h) == 2 && screen_active(h) ? 1 : 0);
+    return per_chunk * ((n_frames + h->chunk - 1) / h->chunk);
 }
 
 int sd_frames_per_launch(sd_handle *h) { return h ? h->chunk : 0; }
 
-int sd_active_variant(sd_handle *h) {
-    if (!h) return 0;
-    const bool fast = h->s.padl && ((h->variant >= 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g)));
-    const bool ws = (h->variant == 3 || (h->variant == 0 && h->auto_ws)) && h->s.padl && !h->dbg_cost && !h->dbg_agg &&
-                    mbm_wta_ws_supported(h->g);
-    return ws ? 3 : (fast ? 2 : 1);
+int sd_active_variant(sd_handle *h) { return h ? active_variant(h) : 0; }
+
+int sd_set_screen(sd_handle *h, int on) {
+    if (!h) return SD_ERR_BAD_ARG;
+    if (on && !h->s.pass_mask)
+        return fail(h, SD_ERR_UNSUPPORTED, "the level screen needs the specialised fused kernel (radii 1/4/10, cost radius 1) and 3 <= L <= 128");
+    h->screen = on != 0;
+    return SD_OK;
+}
+
+int sd_screen_active(sd_handle *h) { return (h && active_variant(h) == 2 && screen_active(h)) ? 1 : 0; }
+
+int sd_screen_stats(sd_handle *h, double *evaluated_fraction, int reset) {
+    if (!h || !evaluated_fraction) return SD_ERR_BAD_ARG;
+    *evaluated_fraction = 1.0;
+    if (!h->s.screen_stats) return SD_OK;
+    DeviceGuard dg(h->device);
+    if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
+    unsigned long long st[2] = {0, 0};
+    if (h->ev_last_valid) SD_CUDA(h, cudaEventSynchronize(h->ev_last));
+    SD_CUDA(h, cudaMemcpy(st, h->s.screen_stats, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st[1] > 0) *evaluated_fraction = (double)st[0] / (double)st[1];
+    if (reset) SD_CUDA(h, cudaMemset(h->s.screen_stats, 0, sizeof(st)));
+    return SD_OK;
 }
 
 int sd_profile_enable(sd_handle *h, int on) {

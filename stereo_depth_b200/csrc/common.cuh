@@ -55,6 +55,7 @@ struct Geom {
 constexpr int kTileH = 32, kTileW = 64;   // pixels per tile of the specialised kernel
 constexpr int kBandRows = 56;             // band rows staged per tile (54 used + 2 only dead work items touch)
 constexpr int kBandLW = 96;               // left band pitch in shared memory (floats)
+constexpr int kScreenBuckets = 8;         // cost classes of the screened tiles (mbm_screen.cu -> mbm_wta_fast.cu)
 struct PadGeom {
     int tiles_x, tiles_y, rows, pwl, pwr, rw, shift_r;
 };
@@ -89,6 +90,13 @@ struct Scratch {
     float *refined;
     float *agg_vol;  // [F][L][Hd*Wd] (plane-major) aggregated volume, only in reference-compat mode (abs_index), else NULL
     float *padl, *padr;  // [F][rows][pwl], [F][rows][pwr] wrap-padded pooled planes (PadGeom), NULL if unsupported
+    // Certified level screen (mbm_screen.cu), all NULL when unsupported:
+    unsigned *pass_mask;              // [F][tiles_y][tiles_x][4] bit m = the fused kernel must run level pair m of that tile
+    int *tile_order;                  // [kScreenBuckets][F*tiles] tile ids bucketed by flagged-pair count (heaviest bucket last)
+    int *bucket_count;                // [kScreenBuckets] tiles per bucket (zeroed before every screen launch)
+    unsigned long long *screen_stats; // [2] {level pairs flagged, level pairs screened} since the last reset
+    int *range_flag;                  // == range_epoch when some pooled value of the current chunk lies outside [0,255]
+    int range_epoch;                  // (or is NaN): the screen's error bound does not hold, masks are ignored
 };
 
 // kernel launchers (each returns cudaGetLastError())
@@ -98,8 +106,11 @@ cudaError_t launch_pad_pooled(const Geom &g, int frames, const Scratch &s, cudaS
 cudaError_t launch_mbm_wta_generic(const Geom &g, int frames, const Scratch &s, float *dbg_cost,
                                    float *dbg_agg, cudaStream_t st);
 bool mbm_wta_fast_supported(const Geom &g);
+// use_screen: run only the level pairs flagged in s.pass_mask (written by launch_mbm_screen for the same chunk)
 cudaError_t launch_mbm_wta_fast(const Geom &g, int frames, const Scratch &s, float *dbg_cost,
-                                float *dbg_agg, cudaStream_t st);
+                                float *dbg_agg, cudaStream_t st, bool use_screen = false);
+bool mbm_screen_supported(const Geom &g);
+cudaError_t launch_mbm_screen(const Geom &g, int frames, const Scratch &s, cudaStream_t st);
 bool mbm_wta_ws_supported(const Geom &g);
 cudaError_t launch_mbm_wta_ws(const Geom &g, int frames, const Scratch &s, cudaStream_t st);
 cudaError_t launch_secondary(const Geom &g, int frames, const Scratch &s, cudaStream_t st);

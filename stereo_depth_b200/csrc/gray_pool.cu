@@ -154,7 +154,8 @@ __device__ __forceinline__ int wrap_near(int i, int n) {
 }
 
 __global__ void __launch_bounds__(256) pad_pooled_kernel(const float *__restrict__ pool, float *__restrict__ padl,
-                                                         float *__restrict__ padr, int Hd, int Wd, PadGeom pg) {
+                                                         float *__restrict__ padr, int Hd, int Wd, PadGeom pg,
+                                                         int *__restrict__ range_flag, int range_epoch) {
     const int c4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int r = blockIdx.y;
     const int frame = blockIdx.z >> 1, side = blockIdx.z & 1;
@@ -168,6 +169,13 @@ __global__ void __launch_bounds__(256) pad_pooled_kernel(const float *__restrict
     v.z = __ldg(src + wrap_near(vc + 2, Wd));
     v.w = __ldg(src + wrap_near(vc + 3, Wd));
     *reinterpret_cast<float4 *>((side ? padr : padl) + ((size_t)frame * pg.rows + r) * pw + c4) = v;
+    // The level screen's error bound needs every similarity tap 255-|l-r| to be >= 0: flag pooled values outside
+    // [0,255] (NaN fails the comparison too).  Cannot happen with uint8 images.
+    if (range_flag) {
+        const float mn = fminf(fminf(v.x, v.y), fminf(v.z, v.w)), mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+        const bool nan = (v.x != v.x) || (v.y != v.y) || (v.z != v.z) || (v.w != v.w);
+        if (nan || !(mn >= 0.0f) || !(mx <= 255.0f)) *range_flag = range_epoch;
+    }
 }
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -202,7 +210,7 @@ cudaError_t launch_pad_pooled(const Geom &g, int frames, const Scratch &s, cudaS
     const PadGeom pg = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
     const int pw = pg.pwl > pg.pwr ? pg.pwl : pg.pwr;
     dim3 grid((pw / 4 + 255) / 256, pg.rows, frames * 2);
-    pad_pooled_kernel<<<grid, 256, 0, st>>>(s.pool, s.padl, s.padr, g.Hd, g.Wd, pg);
+    pad_pooled_kernel<<<grid, 256, 0, st>>>(s.pool, s.padl, s.padr, g.Hd, g.Wd, pg, s.range_flag, s.range_epoch);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,370 @@
+// Kernel S: certified level screen for the specialised fused kernel (mbm_wta_fast.cu).
+//
+// The fused kernel must evaluate every window sum as the reference's sequential fp32 chain (204 adds per
+// (pixel, level) cell) because the arg-max is sensitive to the summation order.  But only the levels that can
+// still BE the arg-max need that treatment.  This kernel computes every aggregated cost approximately -- the same
+// fp32 taps, summed separably (3x3 cost -> nested vertical 3/9/21-row sums -> sliding horizontal 21/9/3-column
+// sums; ~45 lane-ops per cell instead of 237) -- and keeps, per pixel, the set of level pairs whose approximate
+// cost is within a RIGOROUS error bound of the pixel's approximate maximum.  The union over a 32x64 tile, dilated
+// by one pair (the secondary matching reads A[d*-1], A[d*+1]; circular, secondary_matching.cu:28-31), is the
+// tile's pass mask: mbm_wta_fast_kernel then runs its exact passes only for those level pairs.  Results are
+// bit-identical to evaluating all levels (tests/test_gpu_parity.py runs both ways):
+//
+//   * taps  t = 255 - |l - r|  are computed exactly like the reference (device_functions.cuh:66-70), so both sides
+//     sum the SAME fp32 numbers; for pooled values in [0, 255] every tap is >= 0 and every window sum S satisfies
+//     |S_ref - S| <= 89 u S_max and |S_screen - S| <= 60 u S_max  (u = 2^-24, S_max = 63*9*255 resp. 81*9*255):
+//     below 1.5 in absolute terms; the analysis below uses E = 4.
+//   * a pixel whose approximate maximum A'max is >= T = 2^15 * 144600 * 185910 has all three sums of that level
+//     >= F = 2^15, hence A_ref[max] >= A'max (1 - 3.7e-4).  A level with A' < (1 - 2e-3) A'max has
+//     A_ref <= (H'+E)(V'+E)(C'+E)(1+2u) < A'max (1 - 3.7e-4)  (all sums >= F/2: factor (1 + E/(F/2))^3 = 1.00073;
+//     else the product is < 4.41e14 < T/2) -- it cannot be the reference's arg-max and is dropped.
+//   * pixels with A'max < T (never seen on image data: mean tap < 58 of 255) flag every pass of their tile;
+//     out-of-range float inputs (pooled value outside [0, 255] or NaN) are detected by pad_pooled_kernel and
+//     make the fused kernel ignore the masks altogether.
+//
+// Layout: one block per 32x64 tile (the fused kernel's tile), 256 threads = two groups of 128 that share the
+// TMA-staged row bands and screen the even resp. odd level pairs independently (named barriers), each with its
+// own three row-sum buffers.  Phase A: thread = one of the 84 cost columns, walks the 54 band rows with all
+// running sums in registers (all-positive nested sums: Y3 -> Z9 -> W21).  Phase B: thread = (row, 16 columns),
+// sliding sums along the row, product, candidate bookkeeping (running max + bit set with conservative clearing).
+#include "common.cuh"
+#include "mbm_helpers.cuh"
+
+namespace sd {
+namespace {
+
+using namespace mbm;
+
+constexpr int SXW = 84;         // cost columns per tile (64 + 2*10)
+constexpr int SBR = 54;         // band rows used (32 + 2*10 + 2*1)
+constexpr int SPITCH = 86;      // row pitch of the row-sum buffers in float2 cells: 688 B = 5*128 + 48 -> LDS.128 of
+                                // eight consecutive rows hits eight different 16-byte bank groups
+constexpr int SBUF = 32 * SPITCH;           // cells per buffer
+constexpr int SGT = 128;                    // threads per group
+constexpr float kKeep = 0.998f;             // candidate:  A' >= kKeep * running max        (eps  = 2e-3)
+constexpr float kClear = 1.005f;            // new max > kClear * old max clears the set    (eps' = 5e-3 >= eps/(1-eps))
+constexpr float kMinMax = 32768.0f * 144600.0f * 185910.0f;   // T
+
+__host__ __device__ inline size_t screen_smem_bytes(int L, int min_ds) {
+    return (size_t)2 * 3 * SBUF * sizeof(float2) + (size_t)SBR * (LW + make_pad_geom(64, 64, L, min_ds).rw) * 4;
+}
+
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(SGT) : "memory"); }
+
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+
+// ---- phase A: cost column s of level pair (d0, d0+1); Y3 / Z9 / W21 = 3 / 9 / 21-row sums of the 3x3 cost ----------
+// Band row rr holds image row r0-11+rr; cost-plane row R = rr-2 (image row r0-10+R) is complete at step rr.
+// Left band column of (cost column s, dx) = s+5+dx; right band column of (s, dx, level d) = s+dx+Lp-d
+// (same indexing as the cost phase of mbm_wta_fast.cu).  Lane .x = level d0, .y = level d0+1.
+__device__ __forceinline__ void screen_phase_a(const float *__restrict__ pl, const float *__restrict__ pr, int RW,
+                                               float2 *__restrict__ bY, float2 *__restrict__ bZ, float2 *__restrict__ bW) {
+    // Software pipeline with one dependent operation per stage: iteration `it` runs stage E_k on band row it-k-1, and
+    // the stages are listed last-first, so every instruction of an iteration only reads results of EARLIER
+    // iterations (the loop is fully unrolled: all ring indices are compile-time, rings are just names).  Pair sums
+    // (p, q, zb, wb) are formed as soon as their operands exist, which leaves one dependent add per stage:
+    //   E0 loads | E1 a = l-r | E2 t = 255-|a| | E3 u = t0+t1 | E4 h3 = u+t2 | E5 X | E6 Y3 | E7 Z9 | E8 W21
+    //   X(R)   = h3(R) + h3(R+1) + h3(R+2)              3x3 cost of plane row R (band rows R..R+2)
+    //   Y3(c)  = X(c-1) + X(c) + X(c+1)      c in [1,50]
+    //   Z9(c)  = Y3(c-3) + Y3(c) + Y3(c+3)   c in [4,47]
+    //   W21(c) = Z9(c-6) + Y3(c) + Z9(c+6)   c in [10,41]   (the 32 output rows of the tile are plane rows 10..41)
+    float rw[4][7];          // raw band values: l0 l1 l2 | q0 q1 q2 q3
+    float a[4][6];           // l - r per (tap column, level)
+    float2 t[4][3], u[4], h3[4], p[4], X[4], q[4];
+    float2 Y[16], Z[16], zb[16], wb[16];
+#pragma unroll
+    for (int it = 0; it < SBR + 10; it++) {
+        {   // E8: row i delivered Z9(i-6) in the previous iteration -> W21(i-12)
+            const int i = it - 9, cz = i - 6, cw = cz - 6;
+            if (i >= 0 && i < SBR && cw >= 10 && cw <= 41) bW[(cw - 10) * SPITCH] = add2(wb[cw % 16], Z[cz % 16]);
+        }
+        {   // E7: row i delivered Y3(i-3) in the previous iteration
+            const int i = it - 8, cy = i - 3;
+            if (i >= 0 && i < SBR && cy >= 1) {
+                if (cy >= 7) {
+                    const int cz = cy - 3;
+                    Z[cz % 16] = add2(zb[cz % 16], Y[cy % 16]);
+                    if (cz >= 10 && cz <= 41) bZ[(cz - 10) * SPITCH] = Z[cz % 16];
+                }
+                if (cy >= 4) zb[cy % 16] = add2(Y[(cy - 3) % 16], Y[cy % 16]);
+                if (cy >= 10 && cy <= 41) wb[cy % 16] = add2(Z[(cy - 6) % 16], Y[cy % 16]);   // Z9(cy-6) is 3 iterations old
+            }
+        }
+        {   // E6: row i delivered X(i-2) in the previous iteration
+            const int i = it - 7, R = i - 2;
+            if (i >= 0 && i < SBR && R >= 0) {
+                if (R >= 2) {
+                    const int cy = R - 1;
+                    Y[cy % 16] = add2(q[(R - 1) % 4], X[R % 4]);
+                    if (cy >= 10 && cy <= 41) bY[(cy - 10) * SPITCH] = Y[cy % 16];
+                }
+                if (R >= 1) q[R % 4] = add2(X[(R - 1) % 4], X[R % 4]);
+            }
+        }
+        {   // E5: h3(i) is one iteration old
+            const int i = it - 6;
+            if (i >= 0 && i < SBR) {
+                if (i >= 2) X[(i - 2) % 4] = add2(p[(i - 1) % 4], h3[i % 4]);
+                if (i >= 1) p[i % 4] = add2(h3[(i - 1) % 4], h3[i % 4]);
+            }
+        }
+        {   // E4
+            const int i = it - 5;
+            if (i >= 0 && i < SBR) h3[i % 4] = add2(u[i % 4], t[i % 4][2]);
+        }
+        {   // E3
+            const int i = it - 4;
+            if (i >= 0 && i < SBR) u[i % 4] = add2(t[i % 4][0], t[i % 4][1]);
+        }
+        {   // E2: taps, lane .x = level d0, .y = level d0+1 (device_functions.cuh:66-70: 255 - |l - r|)
+            const int i = it - 3;
+            if (i >= 0 && i < SBR) {
+                const float *aa = a[i % 4];
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    t[i % 4][k] = make_float2(__fsub_rn(255.0f, fabsf(aa[2 * k])), __fsub_rn(255.0f, fabsf(aa[2 * k + 1])));
+            }
+        }
+        {   // E1: the loads were issued two iterations ago
+            const int i = it - 2;
+            if (i >= 0 && i < SBR) {
+                const float *w = rw[i % 4];
+                float *aa = a[i % 4];
+                aa[0] = __fsub_rn(w[0], w[4]); aa[1] = __fsub_rn(w[0], w[3]);
+                aa[2] = __fsub_rn(w[1], w[5]); aa[3] = __fsub_rn(w[1], w[4]);
+                aa[4] = __fsub_rn(w[2], w[6]); aa[5] = __fsub_rn(w[2], w[5]);
+            }
+        }
+        if (it < SBR) {   // E0 (volatile asm keeps the loads where they are written: two iterations ahead of their use)
+            float *w = rw[it % 4];
+            const unsigned la = smem_u32(pl + it * LW), ra = smem_u32(pr);
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w[0]) : "r"(la));
+            asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(w[1]) : "r"(la));
+            asm volatile("ld.shared.f32 %0, [%1+8];" : "=f"(w[2]) : "r"(la));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w[3]) : "r"(ra));
+            asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(w[4]) : "r"(ra));
+            asm volatile("ld.shared.f32 %0, [%1+8];" : "=f"(w[5]) : "r"(ra));
+            asm volatile("ld.shared.f32 %0, [%1+12];" : "=f"(w[6]) : "r"(ra));
+            pr += RW;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(2 * SGT, 1)
+mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const float *__restrict__ padr,
+                  unsigned *__restrict__ pass_mask, unsigned long long *__restrict__ stats, int *__restrict__ tile_order,
+                  int *__restrict__ bucket_count) {
+    extern __shared__ float4 smem4[];
+    float2 *bufs = reinterpret_cast<float2 *>(smem4);                   // [2 groups][Y3, Z9, W21][32][SPITCH]
+    float *bandL = reinterpret_cast<float *>(bufs + 2 * 3 * SBUF);      // [SBR][LW]
+    float *bandR = bandL + SBR * LW;                                    // [SBR][RW]
+    __shared__ __align__(8) uint64_t band_bar;
+    __shared__ unsigned s_mask[2];
+    __shared__ int s_all;
+
+    const int tid = threadIdx.x, grp = tid >> 7, gt = tid & (SGT - 1);
+    const int frame = blockIdx.z, r0 = blockIdx.y * kTileH, c0 = blockIdx.x * BW;
+    const int Hd = g.Hd, Wd = g.Wd, L = g.L;
+    const int Lp = (L + 1) & ~1, M = Lp >> 1;
+    const int RW = pg.rw;
+
+    if (tid == 0) {
+        mbar_init(&band_bar, 1);
+        s_mask[0] = s_mask[1] = 0u;
+        s_all = 0;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        if (tid == 0) mbar_expect_tx(&band_bar, (unsigned)(SBR * (LW + RW) * 4));
+        __syncwarp();
+        const float *sl = padl + ((size_t)frame * pg.rows + r0) * pg.pwl + c0;
+        const float *sr = padr + ((size_t)frame * pg.rows + r0) * pg.pwr + c0;
+        for (int rr = tid; rr < SBR; rr += 32) {
+            tma_bulk_g2s(bandL + rr * LW, sl + (size_t)rr * pg.pwl, LW * 4, &band_bar);
+            tma_bulk_g2s(bandR + rr * RW, sr + (size_t)rr * pg.pwr, (unsigned)(RW * 4), &band_bar);
+        }
+    }
+
+    float2 *bY = bufs + grp * 3 * SBUF, *bZ = bY + SBUF, *bW = bZ + SBUF;
+    // phase-B ownership: pooled row `row` of the tile, columns 16*seg .. 16*seg+15 (a warp = one segment: its 32
+    // lanes read 32 different rows, conflict-free with SPITCH)
+    const int row = gt & 31, seg = gt >> 5;
+    float rmax[16], lo[16];
+    unsigned cand[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const bool valid = (r0 + row < Hd) && (c0 + 16 * seg + k < Wd);
+        rmax[k] = 0.0f;
+        lo[k] = valid ? 0.0f : __int_as_float(0x7f800000);   // pixels outside the image never become candidates
+        cand[k] = 0u;
+    }
+
+    {
+        int spins = 0;
+        while (!mbar_try_wait(&band_bar, 0))
+            if (++spins > (1 << 24)) __trap();  // a lost transaction must not hang the GPU
+    }
+
+    for (int m = grp; m < M; m += 2) {
+        const int d0 = 2 * m;
+        if (gt < SXW) screen_phase_a(bandL + gt + 4, bandR + gt + (Lp - d0 - 2), RW, bY + gt, bZ + gt, bW + gt);
+        group_sync(grp);
+
+        // ---- phase B ---------------------------------------------------------------------------------------
+        // Sliding sums along the row: the first window is a tree sum, every further output is one dependent add of
+        // a precomputed difference (entering - leaving cell), so the H and C recurrences are two short chains that
+        // interleave.  Absolute error of a window sum <= (5 + 2*15) u S_max (see the header).
+        const float2 neg1 = make_float2(-1.0f, -1.0f);
+        float2 dh[16], dc[16], V[16];
+        {   // H = 21-column sum of Y3: cost columns y .. y+20 for tile column y
+            const float4 *pp = reinterpret_cast<const float4 *>(bY + row * SPITCH + 16 * seg);
+            float2 y[36];
+#pragma unroll
+            for (int j = 0; j < 18; j++) {
+                const float4 v4 = pp[j];
+                y[2 * j] = lo2(v4);
+                y[2 * j + 1] = hi2(v4);
+            }
+            float2 s1[10], s2[5];
+#pragma unroll
+            for (int j = 0; j < 10; j++) s1[j] = add2(y[2 * j], y[2 * j + 1]);
+#pragma unroll
+            for (int j = 0; j < 5; j++) s2[j] = add2(s1[2 * j], s1[2 * j + 1]);
+            dh[0] = add2(add2(add2(s2[0], s2[1]), add2(s2[2], s2[3])), add2(s2[4], y[20]));
+#pragma unroll
+            for (int k = 1; k < 16; k++) dh[k] = __ffma2_rn(y[k - 1], neg1, y[k + 20]);   // y[k+20] - y[k-1], one rounding
+        }
+        {   // C = 9-column sum of Z9: cost columns y+6 .. y+14
+            const float4 *pp = reinterpret_cast<const float4 *>(bZ + row * SPITCH + 16 * seg + 6);
+            float2 z[24];
+#pragma unroll
+            for (int j = 0; j < 12; j++) {
+                const float4 v4 = pp[j];
+                z[2 * j] = lo2(v4);
+                z[2 * j + 1] = hi2(v4);
+            }
+            dc[0] = add2(add2(add2(z[0], z[1]), add2(z[2], z[3])), add2(add2(z[4], z[5]), add2(add2(z[6], z[7]), z[8])));
+#pragma unroll
+            for (int k = 1; k < 16; k++) dc[k] = __ffma2_rn(z[k - 1], neg1, z[k + 8]);
+        }
+        {   // V = W21[y+9] + W21[y+10] + W21[y+11]
+            const float4 *pp = reinterpret_cast<const float4 *>(bW + row * SPITCH + 16 * seg + 8);
+            float2 w[20];
+#pragma unroll
+            for (int j = 0; j < 10; j++) {
+                const float4 v4 = pp[j];
+                w[2 * j] = lo2(v4);
+                w[2 * j + 1] = hi2(v4);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++) V[k] = add2(add2(w[k + 1], w[k + 2]), w[k + 3]);
+        }
+        float2 A[16];
+        {
+            float2 h = dh[0], c = dc[0];
+            A[0] = __fmul2_rn(__fmul2_rn(h, V[0]), c);
+#pragma unroll
+            for (int k = 1; k < 16; k++) {
+                h = add2(h, dh[k]);
+                c = add2(c, dc[k]);
+                A[k] = __fmul2_rn(__fmul2_rn(h, V[k]), c);
+            }
+        }
+        // ---- candidate bookkeeping: the set always contains every level pair within kKeep of the final maximum
+        const bool has2 = (d0 + 1 < L);
+        const unsigned bit = 1u << (m >> 1);
+        float v[16];
+        bool hit = false;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            v[k] = has2 ? fmaxf(A[k].x, A[k].y) : A[k].x;
+            hit |= (v[k] >= lo[k]);
+        }
+        if (hit) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                if (v[k] >= lo[k]) {
+                    if (v[k] > rmax[k] * kClear) cand[k] = 0u;   // everything seen so far is below (1-eps) of the new max
+                    cand[k] |= bit;
+                    if (v[k] > rmax[k]) {
+                        rmax[k] = v[k];
+                        lo[k] = v[k] * kKeep;
+                    }
+                }
+            }
+        }
+        group_sync(grp);   // the buffers are free for the next pass of this group
+    }
+
+    // ---- merge the two groups' candidate sets (they screened disjoint level pairs) --------------------------------
+    __syncthreads();
+    float *xm = reinterpret_cast<float *>(bufs);   // [2][32*64] running maxima, aliases the (now idle) buffers
+#pragma unroll
+    for (int k = 0; k < 16; k++) xm[grp * 2048 + row * 64 + 16 * seg + k] = rmax[k];
+    __syncthreads();
+    unsigned mine = 0u;
+    bool weak = false;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const bool valid = (r0 + row < Hd) && (c0 + 16 * seg + k < Wd);
+        if (!valid) continue;
+        const float other = xm[(grp ^ 1) * 2048 + row * 64 + 16 * seg + k];
+        if (!(other > rmax[k] * kClear)) mine |= cand[k];   // else: none of this group's pairs is within eps of the max
+        if (!(fmaxf(other, rmax[k]) >= kMinMax)) weak = true;   // bound not applicable (also catches NaN)
+    }
+    mine = __reduce_or_sync(0xffffffffu, mine);
+    weak = __any_sync(0xffffffffu, weak);
+    if ((tid & 31) == 0) {
+        if (mine) atomicOr(&s_mask[grp], mine);
+        if (weak) atomicOr(&s_all, 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned w[4] = {0u, 0u, 0u, 0u};
+        if (s_all) {
+            for (int m = 0; m < M; m++) w[m >> 5] |= 1u << (m & 31);
+        } else {
+            for (int m = 0; m < M; m++) {
+                if (!((s_mask[m & 1] >> (m >> 1)) & 1u)) continue;
+                const int a = (m + M - 1) % M, b = (m + 1) % M;   // circular dilation by one pair
+                w[m >> 5] |= 1u << (m & 31);
+                w[a >> 5] |= 1u << (a & 31);
+                w[b >> 5] |= 1u << (b & 31);
+            }
+        }
+        const int tile = (frame * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        unsigned *dst = pass_mask + (size_t)tile * 4;
+        dst[0] = w[0]; dst[1] = w[1]; dst[2] = w[2]; dst[3] = w[3];
+        const int pc = __popc(w[0]) + __popc(w[1]) + __popc(w[2]) + __popc(w[3]);
+        // cost class of the tile for the fused kernel's heaviest-first schedule
+        const int b = (pc * kScreenBuckets) / (M + 1);
+        tile_order[b * (gridDim.x * gridDim.y * gridDim.z) + atomicAdd(&bucket_count[b], 1)] = tile;
+        if (stats) {
+            atomicAdd(&stats[0], (unsigned long long)pc);
+            atomicAdd(&stats[1], (unsigned long long)M);
+        }
+    }
+}
+
+}  // namespace
+
+bool mbm_screen_supported(const Geom &g) {
+    const int Lp = (g.L + 1) & ~1;
+    return mbm_wta_fast_supported(g) && Lp / 2 <= 64 && Lp / 2 >= 2 && screen_smem_bytes(g.L, g.min_ds) <= 227 * 1024;
+}
+
+cudaError_t launch_mbm_screen(const Geom &g, int frames, const Scratch &s, cudaStream_t st) {
+    if (!mbm_screen_supported(g) || !s.padl || !s.padr || !s.pass_mask || !s.tile_order || !s.bucket_count) return cudaErrorNotSupported;
+    const size_t smem = screen_smem_bytes(g.L, g.min_ds);
+    const PadGeom pg = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
+    cudaError_t e = cudaFuncSetAttribute(mbm_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid(pg.tiles_x, pg.tiles_y, frames);
+    e = cudaMemsetAsync(s.bucket_count, 0, kScreenBuckets * sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    mbm_screen_kernel<<<grid, 2 * SGT, smem, st>>>(g, pg, s.padl, s.padr, s.pass_mask, s.screen_stats, s.tile_order,
+                                                   s.bucket_count);
+    return cudaGetLastError();
+}
+
+}  // namespace sd

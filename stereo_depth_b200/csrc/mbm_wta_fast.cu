@@ -55,7 +55,9 @@ template <int BH, bool DBG, int MODE, bool STORE>
 __global__ void __launch_bounds__(Cfg<BH>::NT, (BH <= 32) ? 2 : 1)
 mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const float *__restrict__ padr,
                     float4 *__restrict__ wta4, float2 *__restrict__ edge2, float *__restrict__ dbg_cost,
-                    float *__restrict__ dbg_agg, float *__restrict__ agg_planes) {
+                    float *__restrict__ dbg_agg, float *__restrict__ agg_planes, const unsigned *__restrict__ pass_mask,
+                    const int *__restrict__ range_flag, int range_epoch, const int *__restrict__ tile_order,
+                    const int *__restrict__ bucket_count) {
     using C = Cfg<BH>;
     extern __shared__ float4 smem4[];
     float4 *plane = smem4;                                              // [PRW][42] chunks of (cell,level) pairs
@@ -63,7 +65,25 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
     float *bandR = bandL + C::BR * LW;                                  // [BR][RW]
 
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int frame = blockIdx.z, r0 = blockIdx.y * BH, c0 = blockIdx.x * BW;
+    // Which tile: by default the block's own coordinates.  Behind the level screen the tiles differ widely in cost
+    // (3 .. M level pairs), so the screen sorts them into 8 buckets by pair count and blocks take them heaviest first
+    // (longest-processing-time order: no long tile is left to start last).
+    int tile = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (tile_order) {
+        const int nt = gridDim.x * gridDim.y * gridDim.z;
+        int rem = tile;
+#pragma unroll
+        for (int b = kScreenBuckets - 1; b >= 0; b--) {
+            const int c = bucket_count[b];
+            if (rem < c) {
+                tile = tile_order[b * nt + rem];
+                break;
+            }
+            rem -= c;
+        }
+    }
+    const int tile_x = tile % gridDim.x, tile_y = (tile / gridDim.x) % gridDim.y;
+    const int frame = tile / (gridDim.x * gridDim.y), r0 = tile_y * BH, c0 = tile_x * BW;
     const int Hd = g.Hd, Wd = g.Wd, L = g.L;
     const int Lp = (L + 1) & ~1, M = Lp >> 1;
     const size_t np = (size_t)Hd * Wd;
@@ -73,7 +93,16 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
     // The wrap-padded planes (pad_pooled_kernel) make every band row one contiguous 16-byte aligned segment:
     // one cp.async.bulk per row and view, completion counted in bytes on an mbarrier.
     __shared__ __align__(8) uint64_t band_bar;
+    // Level pairs this tile has to evaluate (certified screen, mbm_screen.cu); all of them without a screen or
+    // when the screen's precondition (pooled values in [0,255]) does not hold for this chunk.
+    __shared__ unsigned s_pass[4];
     if (tid == 0) mbar_init(&band_bar, 1);
+    if (tid < 4) {
+        unsigned w = 0xffffffffu;
+        if (pass_mask && *range_flag != range_epoch)
+            w = pass_mask[(size_t)tile * 4 + tid];
+        s_pass[tid] = w;
+    }
     __syncthreads();
     if (tid < 32) {
         if (tid == 0) mbar_expect_tx(&band_bar, (unsigned)(C::BR * (LW + RW) * 4));
@@ -113,6 +142,9 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
     }
 
     for (int m = 0; m < M; m++) {
+        // Skipped level pairs leave prev[] / pend stale.  That only ever reaches records that a later level
+        // overwrites: the reference's arg-max d* is always evaluated together with d*-1 and d*+1 (circular).
+        if (!((s_pass[(m >> 5) & 3] >> (m & 31)) & 1u)) continue;
         const int d0 = 2 * m;
         // ================= cost phase: plane[R][s] = (cost(d0), cost(d0+1)) ==========================
         // The right band is read at column offset e = Lp-2-d0 (even): 16-byte aligned on every other
@@ -410,15 +442,17 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
 }
 
 template <int BH, bool DBG, int MODE, bool STORE>
-cudaError_t launch_t(const Geom &g, int frames, const Scratch &s, float *dbg_cost, float *dbg_agg, cudaStream_t st) {
+cudaError_t launch_t(const Geom &g, int frames, const Scratch &s, float *dbg_cost, float *dbg_agg, cudaStream_t st,
+                     bool use_screen = false) {
     const size_t smem = smem_bytes<BH>(g.L, g.min_ds);
     const PadGeom pg = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
     // per-device attribute: set on every launch (cheap) so multi-GPU processes stay correct
     cudaError_t e = cudaFuncSetAttribute(mbm_wta_fast_kernel<BH, DBG, MODE, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((g.Wd + BW - 1) / BW, (g.Hd + BH - 1) / BH, frames);
-    mbm_wta_fast_kernel<BH, DBG, MODE, STORE><<<grid, Cfg<BH>::NT, smem, st>>>(g, pg, s.padl, s.padr, s.wta4, s.edge2,
-                                                                                dbg_cost, dbg_agg, s.agg_vol);
+    mbm_wta_fast_kernel<BH, DBG, MODE, STORE><<<grid, Cfg<BH>::NT, smem, st>>>(
+        g, pg, s.padl, s.padr, s.wta4, s.edge2, dbg_cost, dbg_agg, s.agg_vol, use_screen ? s.pass_mask : nullptr,
+        s.range_flag, s.range_epoch, use_screen ? s.tile_order : nullptr, s.bucket_count);
     return cudaGetLastError();
 }
 
@@ -441,18 +475,23 @@ bool mbm_wta_fast_supported(const Geom &g) {
 }
 
 cudaError_t launch_mbm_wta_fast(const Geom &g, int frames, const Scratch &s, float *dbg_cost, float *dbg_agg,
-                                cudaStream_t st) {
+                                cudaStream_t st, bool use_screen) {
     if (!mbm_wta_fast_supported(g) || !s.padl || !s.padr) return cudaErrorNotSupported;
     {
         cudaError_t e = launch_pad_pooled(g, frames, s, st);
         if (e != cudaSuccess) return e;
     }
+    // the debug / reference-compat modes need every level of the volume: no screen there
     if (dbg_cost || dbg_agg) return launch_t<32, true, 0, true>(g, frames, s, dbg_cost, dbg_agg, st);
     if (s.agg_vol) return launch_t<32, false, 2, true>(g, frames, s, nullptr, nullptr, st);
+    if (use_screen) {
+        cudaError_t e = launch_mbm_screen(g, frames, s, st);
+        if (e != cudaSuccess) return e;
+    }
     switch (fast_mode()) {
-        case 1: return launch_t<32, false, 1, false>(g, frames, s, nullptr, nullptr, st);
-        case 2: return launch_t<32, false, 2, false>(g, frames, s, nullptr, nullptr, st);
-        default: return launch_t<32, false, 0, false>(g, frames, s, nullptr, nullptr, st);
+        case 1: return launch_t<32, false, 1, false>(g, frames, s, nullptr, nullptr, st, use_screen);
+        case 2: return launch_t<32, false, 2, false>(g, frames, s, nullptr, nullptr, st, use_screen);
+        default: return launch_t<32, false, 0, false>(g, frames, s, nullptr, nullptr, st, use_screen);
     }
 }
 

@@ -161,6 +161,17 @@ class StereoMatching:
     def set_variant(self, v):
         self._handle.set_variant({"auto": 0, "generic": 1, "fast": 2, "ws": 3}.get(v, v))
 
+    def set_screen(self, on=True):
+        """Certified level screen in front of the fused kernel (default on where supported; results identical)."""
+        self._handle.set_screen(on)
+
+    @property
+    def screen_active(self):
+        return self._handle.screen_active
+
+    def screen_stats(self, reset=True):
+        return self._handle.screen_stats(reset)
+
     def profile(self, on=True):
         self._handle.profile_enable(on)
 

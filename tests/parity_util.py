@@ -42,7 +42,7 @@ def oracle_config_from_array(O, arr):
 
 
 def run_cuda_all_stages(left_u8, right_u8, cfg_kwargs, variant="auto", dtype="u8", volumes=True, frames_per_launch=0,
-                        compat=None):
+                        compat=None, screen=None, info=None):
     """Runs the CUDA path on one frame and returns every intermediate as numpy arrays."""
     import torch
     from stereo_depth_b200 import cuda_depth
@@ -51,7 +51,11 @@ def run_cuda_all_stages(left_u8, right_u8, cfg_kwargs, variant="auto", dtype="u8
     sm.set_variant(variant)
     if compat is not None:
         sm.set_compat(compat)
+    if screen is not None:
+        sm.set_screen(screen)
     vols = sm.debug_volumes(True) if volumes else None
+    if info is not None:
+        info["screen_active"] = sm.screen_active
     l = torch.from_numpy(left_u8).cuda()
     r = torch.from_numpy(right_u8).cuda()
     if dtype == "f32":
@@ -63,6 +67,8 @@ def run_cuda_all_stages(left_u8, right_u8, cfg_kwargs, variant="auto", dtype="u8
         res[st] = sm.stage(st).cpu().numpy()
     if vols:
         res["cost"], res["agg"] = vols[0].cpu().numpy(), vols[1].cpu().numpy()
+    if info is not None:
+        info["evaluated_fraction"] = sm.screen_stats()
     return res
 
 

@@ -4,6 +4,8 @@
   * the reference's own kernel outputs (tests/golden/*.npz) wherever the reference is defined.
 north_star tolerance: bit-exact for pooled images, costs and WTA disparities, <= 1e-3 px for the refined
 and filled float disparities.  We assert bit-exactness for those too (TOL_PX documents the contract)."""
+import zlib
+
 import numpy as np
 import pytest
 
@@ -71,6 +73,87 @@ def test_seeded_bit_exact_vs_oracle(shape, variant):
         assert max_abs(got["out"], ref["out"]) <= TOL_PX
 
 
+SCREENABLE = [sh for sh in SEEDED if 3 <= sh[4] // sh[2] - sh[3] // sh[2] + 1 <= 128 and sh[3] // sh[2] == 0]
+
+
+@pytest.mark.parametrize("shape", SCREENABLE)
+@pytest.mark.parametrize("dtype", ["u8", "f32"])
+def test_screened_bit_exact_vs_oracle(shape, dtype):
+    """Certified level screen on (mbm_screen.cu): the fused kernel evaluates only the flagged level pairs and must
+    still produce the oracle's WTA records, refined and filled disparities bit for bit."""
+    H, W, K, mn, mx = shape
+    kw = cfg_kw(H, W, K, mn, mx)
+    l, r, _ = make_pair(H, W, mx + 1, seed=100 + H)
+    ref = oracle_all(kw, l, r)
+    info = {}
+    got = run_cuda_all_stages(l, r, kw, variant="fast", dtype=dtype, volumes=False, screen=True, info=info)
+    assert info["screen_active"]
+    assert 0.0 < info["evaluated_fraction"] <= 1.0
+    for st in ("wta", "agg3", "refined", "out"):
+        assert mismatch(got[st], ref[st]) == 0, (st, dtype, info)
+
+
+def _textured_scene(rng, H, W, kind):
+    """Float images in [0,255] that stress the screen's candidate logic: near-ties and exact ties."""
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    if kind == "smooth":        # low texture: many levels within a fraction of a percent of the maximum
+        base = 120 + 60 * np.sin(xx / 37.0) * np.cos(yy / 23.0) + rng.normal(0, 0.7, (H, W))
+    elif kind == "stripes":     # periodic: several exact or near-exact maxima per pixel
+        base = 128 + 100 * np.sign(np.sin(xx * (2 * np.pi / 12.0))) + rng.normal(0, 0.05, (H, W))
+    elif kind == "flat":        # constant patches with a few dots
+        base = np.full((H, W), 77.25, np.float32) + (rng.random((H, W)) < 0.01) * 90
+    else:                       # dark vs bright: small similarity sums (screen floor), still in range
+        base = rng.random((H, W)) * 6
+    left = np.clip(np.stack([base, base * 0.9 + 5, base * 0.8 + 11]), 0, 255).astype(np.float32)
+    shift = int(rng.integers(1, 9))
+    right = np.roll(left, -shift, axis=2).copy()
+    if kind == "dark":
+        right = np.clip(255 - right, 0, 255).astype(np.float32)
+    return left, right
+
+
+@pytest.mark.parametrize("kind", ["smooth", "stripes", "flat", "dark"])
+@pytest.mark.parametrize("K,D", [(2, 64), (1, 40), (2, 256)])
+def test_screen_on_equals_screen_off_hard_scenes(kind, K, D):
+    """Low-texture, periodic, flat and very dissimilar scenes: screen on == screen off == oracle, and the screen
+    falls back to evaluating (nearly) everything where it cannot exclude levels."""
+    H, W = 150 * K, 232 * K
+    rng = np.random.default_rng(zlib.crc32(f"{kind}-{K}-{D}".encode()))
+    l, r = _textured_scene(rng, H, W, kind)
+    kw = cfg_kw(H, W, K, 0, D - 1)
+    ref = O.run(O.make_config(**kw), l, r, want=("wta", "refined", "out"))
+    info = {}
+    on = run_cuda_all_stages(l, r, kw, variant="fast", dtype="f32", volumes=False, screen=True, info=info)
+    off = run_cuda_all_stages(l, r, kw, variant="fast", dtype="f32", volumes=False, screen=False)
+    assert info["screen_active"]
+    for st in ("wta", "agg3", "refined", "out"):
+        assert mismatch(on[st], off[st]) == 0, (st, kind, info)
+    for st in ("wta", "refined", "out"):
+        assert mismatch(on[st], ref[st]) == 0, (st, kind, info)
+    if kind in ("flat", "dark"):
+        assert info["evaluated_fraction"] > (0.9 if kind == "dark" else 0.5), info
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_screened_matches_reference_fixtures(name):
+    """Screened CUDA path vs the reference's own kernel outputs (untainted cells)."""
+    g = load_golden(name)
+    kw = {f: int(v) for f, v in zip(O.CONFIG_FIELDS, g["config"])}
+    if kw["min_disparity"] // kw["downscale_factor"]:
+        pytest.skip("reference-compat mode materialises the volume: the screen is off there")
+    L = g["agg"].shape[2]
+    if not 3 <= L <= 128 or kw["ncc_patch_radius"] != 1:
+        pytest.skip("screen unsupported for this configuration")
+    cfg = oracle_config_from_array(O, g["config"])
+    t = O.run(cfg, g["left"], g["right"], mode=O.MODE_SAFE, want=("taint_agg", "taint_refined", "taint_out"))
+    info = {}
+    got = run_cuda_all_stages(g["left"], g["right"], kw, variant="fast", dtype="f32", volumes=False, screen=True, info=info)
+    assert info["screen_active"]
+    assert mismatch(got["wta"], g["wta"], (t["taint_agg"] & 3) == 0) == 0
+    assert mismatch(got["refined"], g["refined"], (t["taint_refined"] & 3) == 0) == 0
+    assert mismatch(got["out"], g["out_api"], (t["taint_out"] & 3) == 0) == 0
+
+
 def test_generic_radii_vs_oracle():
     """Non-default radii go through the generic fused kernel."""
     kw = cfg_kw(80, 144, 2, 0, 23, ncc_patch_radius=2, sad_patch_radius=3, threshold=2,
@@ -121,8 +204,13 @@ def test_full_size_c3_vs_oracle():
     l, r, _ = make_pair(H, W, D, seed=1234)
     cfg = O.make_config(**kw)
     ref = O.run(cfg, l, r, want=("pool_l", "wta", "refined", "out"))
-    got = run_cuda_all_stages(l, r, kw, variant="fast", volumes=False)
+    info = {}
+    got = run_cuda_all_stages(l, r, kw, variant="fast", volumes=False, info=info)
     for st in ("pool_l", "wta", "refined", "out"):
+        assert mismatch(got[st], ref[st]) == 0, st
+    assert info["screen_active"] and info["evaluated_fraction"] < 0.5, info   # the screen is on by default
+    got = run_cuda_all_stages(l, r, kw, variant="fast", volumes=False, screen=False)
+    for st in ("wta", "refined", "out"):
         assert mismatch(got[st], ref[st]) == 0, st
 
 
@@ -214,7 +302,11 @@ def test_batches_chunks_and_host_path_agree():
     assert mismatch(host.numpy(), singles) == 0
     assert mismatch(f32, singles) == 0
     assert mismatch(singles[4], ref) == 0
-    assert be.native.launches_per_call(n) == 5 * 3   # 5 kernels per chunk (incl. the plane-padding kernel), 3 chunks
+    # 6 kernels per chunk (gray+pool, plane padding, level screen, cost+agg+WTA, secondary, fill), 3 chunks
+    assert be.native.screen_active and be.native.launches_per_call(n) == 6 * 3
+    be.native.set_screen(False)
+    assert be.native.launches_per_call(n) == 5 * 3
+    assert mismatch(be.process_batch(torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()).cpu().numpy(), singles) == 0
 
 
 def test_reference_api_semantics():
@@ -394,9 +486,11 @@ def test_fuzz_float_inputs_all_variants(seed):
     mode = O.MODE_COMPAT if mn // K else O.MODE_SAFE
     ref = O.run(O.make_config(**kw), left, right, mode=mode, want=("pool_l", "wta", "refined", "out"))
     lt, rt = torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda()
-    for variant in ("generic", "fast", "ws"):
+    for variant in ("generic", "fast", "ws", "fast-unscreened"):
         sm = cuda_depth.StereoMatching(cuda_depth.StereoMatchingConfiguration(**kw))
-        sm.set_variant(variant)
+        sm.set_variant(variant.split("-")[0])
+        if variant == "fast-unscreened":
+            sm.set_screen(False) if sm.screen_active else None
         out = sm.compute_disparity_map(lt, rt).cpu().numpy()
         for st, got in (("pool_l", sm.stage("pool_l").cpu().numpy()), ("wta", sm.stage("wta").cpu().numpy()),
                         ("refined", sm.stage("refined").cpu().numpy()), ("out", out)):

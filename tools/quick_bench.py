@@ -25,6 +25,8 @@ for name in names:
         sm = cuda_depth.StereoMatching(cuda_depth.StereoMatchingConfiguration(
             height=H, width=W, downscale_factor=K, min_disparity=mind, max_disparity=D - 1), frames_per_launch=nf)
         sm.set_variant(variant)
+        if os.environ.get("SCREEN") is not None and variant == "fast":
+            sm.set_screen(os.environ["SCREEN"] == "1")
         out = sm.compute_disparity_batch(l, r)
         torch.cuda.synchronize()
         reps = 3 if variant == "generic" else 10
@@ -41,5 +43,6 @@ for name in names:
         sm.profile(False)
         Hd, Wd, L = sm.dims
         ops = 237.0 * Hd * Wd * L
+        print(f"screen={sm.screen_active} evaluated_fraction={sm.screen_stats():.3f}", end="  ")
         print(f"{name} {variant}: {ms:.4f} ms/frame  {1000/ms:.1f} fps  (kernel-B algorithmic {ops/1e9:.2f} Gop -> "
               f"{ops/ms/1e9:.1f} Top/s if B were everything)  per-frame kernel ms: {prof}  B: {ops/prof['cost_agg_wta']/1e9:.1f} Top/s", flush=True)
