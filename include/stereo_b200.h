@@ -155,6 +155,9 @@ int sd_active_variant(sd_handle *h);
  * milliseconds and launch counts per kernel ([4] each) since the previous read, and resets them. */
 int sd_profile_enable(sd_handle *h, int on);
 int sd_profile_read(sd_handle *h, double *ms_per_kernel, int *launches_per_kernel);
+/* Same, with kernel 1 split into its launches: [6] each = gray+pool, plane padding, level screen, cost+aggregation+WTA
+ * (exact evaluation), secondary matching, upscale+fill.  Either read resets the counters. */
+int sd_profile_read_detail(sd_handle *h, double *ms_per_kernel, int *launches_per_kernel);
 /* ---- consumers of the disparity map (stateless; device pointers; asynchronous on cuda_stream) --------------
  * Accuracy metrics of depth_estimation_pipeline_metrics.py:18-56 over the mask `0 < gt <= max_disparity`
  * (depth_estimation_pipeline_runner.py:85): metrics_out[4] doubles in device memory =

@@ -19,7 +19,7 @@ CONFIG_FIELDS = ("height", "width", "downscale_factor", "min_disparity", "max_di
 # every symbol include/stereo_b200.h declares
 EXPORTS = ("sd_abi_version", "sd_config_default", "sd_dims", "sd_create", "sd_destroy", "sd_compute",
            "sd_compute_range", "sd_set_band", "sd_compute_host", "sd_get_stage", "sd_set_debug_volumes", "sd_set_compat", "sd_set_variant",
-           "sd_launches_per_call", "sd_frames_per_launch", "sd_active_variant", "sd_set_screen", "sd_screen_active", "sd_screen_stats", "sd_profile_enable", "sd_profile_read", "sd_metrics", "sd_point_cloud",
+           "sd_launches_per_call", "sd_frames_per_launch", "sd_active_variant", "sd_set_screen", "sd_screen_active", "sd_screen_stats", "sd_profile_enable", "sd_profile_read", "sd_profile_read_detail", "sd_metrics", "sd_point_cloud",
            "sd_last_error", "sd_last_cuda_error")
 
 
@@ -70,6 +70,7 @@ def lib():
     L.sd_screen_stats.argtypes = [vp, C.POINTER(C.c_double), ip]
     L.sd_profile_enable.argtypes = [vp, ip]
     L.sd_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.sd_profile_read_detail.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.sd_metrics.argtypes = [vp, vp, C.c_longlong, C.c_float, C.c_float, vp, vp]
     L.sd_point_cloud.argtypes = [vp, ip, ip, C.c_float, C.c_float, vp, vp, vp]
     L.sd_last_error.argtypes = [vp]
@@ -161,6 +162,12 @@ class Handle:
         ms, n = (C.c_double * 4)(), (C.c_int * 4)()
         self.check(lib().sd_profile_read(self._h, ms, n))
         names = ("gray_pool", "cost_agg_wta", "secondary", "fill")
+        return {k: (ms[i], n[i]) for i, k in enumerate(names)}
+
+    def profile_read_detail(self):
+        ms, n = (C.c_double * 6)(), (C.c_int * 6)()
+        self.check(lib().sd_profile_read_detail(self._h, ms, n))
+        names = ("gray_pool", "pad_planes", "level_screen", "cost_agg_wta", "secondary", "fill")
         return {k: (ms[i], n[i]) for i, k in enumerate(names)}
 
     @property

@@ -13,6 +13,7 @@ using namespace sd;
 
 namespace {
 constexpr int kSlots = 4;  // host pipeline depth (H2D / compute / D2H in flight)
+constexpr int kProfMarks = 7;  // start | gray+pool | plane padding | level screen | cost+agg+WTA | secondary | fill
 }
 
 struct sd_handle {
@@ -37,7 +38,7 @@ struct sd_handle {
     // scratch is shared by every call on this handle: each call's stream first waits for the previous call's work
     cudaEvent_t ev_last;
     bool ev_last_valid;
-    // optional per-kernel timing (sd_profile_enable): 5 events per chunk on the launching stream
+    // optional per-kernel timing (sd_profile_enable): kProfMarks events per chunk on the launching stream
     bool prof;
     std::vector<cudaEvent_t> *prof_events;
     char err[320];
@@ -159,8 +160,13 @@ int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int 
         // (reference-compat mode: the kernels also materialise the aggregated volume into h->s.agg_vol)
         h->s.range_epoch = ++h->epoch;
         const int v = active_variant(h);
-        if (v == 3) SD_CUDA(h, launch_mbm_wta_ws(h->g, frames, h->s, st));
-        else if (v == 2) SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st, screen_active(h)));
+        const bool screen = (v == 2) && screen_active(h);
+        if (v == 2) SD_CUDA(h, launch_pad_pooled(h->g, frames, h->s, st));
+        if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
+        if (screen) SD_CUDA(h, launch_mbm_screen(h->g, frames, h->s, st));
+        if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
+        if (v == 3) SD_CUDA(h, launch_mbm_wta_ws(h->g, frames, h->s, st));   // (pads its planes itself)
+        else if (v == 2) SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st, screen));
         else SD_CUDA(h, launch_mbm_wta_generic(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
     }
     if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
@@ -579,26 +585,41 @@ int sd_profile_enable(sd_handle *h, int on) {
     return SD_OK;
 }
 
-int sd_profile_read(sd_handle *h, double *ms, int *launches) {
-    if (!h || !ms || !launches) return SD_ERR_BAD_ARG;
+static int profile_collect(sd_handle *h, double *ms6, int *n6) {
     DeviceGuard dg(h->device);
     std::vector<cudaEvent_t> &ev = *h->prof_events;
-    for (int k = 0; k < 4; k++) {
-        ms[k] = 0.0;
-        launches[k] = 0;
+    for (int k = 0; k < kProfMarks - 1; k++) {
+        ms6[k] = 0.0;
+        n6[k] = 0;
     }
     if (!ev.empty()) SD_CUDA(h, cudaEventSynchronize(ev.back()));
-    for (size_t i = 0; i + 4 < ev.size(); i += 5) {
-        for (int k = 0; k < 4; k++) {
+    for (size_t i = 0; i + kProfMarks <= ev.size(); i += kProfMarks) {
+        for (int k = 0; k < kProfMarks - 1; k++) {
             float t = 0.f;
             SD_CUDA(h, cudaEventElapsedTime(&t, ev[i + k], ev[i + k + 1]));
-            ms[k] += t;
-            launches[k] += 1;
+            ms6[k] += t;
+            n6[k] += 1;
         }
     }
     for (cudaEvent_t e : ev) cudaEventDestroy(e);
     ev.clear();
     return SD_OK;
+}
+
+int sd_profile_read(sd_handle *h, double *ms, int *launches) {
+    if (!h || !ms || !launches) return SD_ERR_BAD_ARG;
+    double m6[kProfMarks - 1];
+    int n6[kProfMarks - 1];
+    const int rc = profile_collect(h, m6, n6);
+    if (rc != SD_OK) return rc;
+    ms[0] = m6[0]; ms[1] = m6[1] + m6[2] + m6[3]; ms[2] = m6[4]; ms[3] = m6[5];
+    launches[0] = n6[0]; launches[1] = n6[3]; launches[2] = n6[4]; launches[3] = n6[5];
+    return SD_OK;
+}
+
+int sd_profile_read_detail(sd_handle *h, double *ms, int *launches) {
+    if (!h || !ms || !launches) return SD_ERR_BAD_ARG;
+    return profile_collect(h, ms, launches);
 }
 
 const char *sd_last_error(sd_handle *h) { return h ? h->err : "null handle"; }

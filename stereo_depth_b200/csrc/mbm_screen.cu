@@ -37,16 +37,21 @@ using namespace mbm;
 
 constexpr int SXW = 84;         // cost columns per tile (64 + 2*10)
 constexpr int SBR = 54;         // band rows used (32 + 2*10 + 2*1)
-constexpr int SPITCH = 86;      // row pitch of the row-sum buffers in float2 cells: 688 B = 5*128 + 48 -> LDS.128 of
-                                // eight consecutive rows hits eight different 16-byte bank groups
-constexpr int SBUF = 32 * SPITCH;           // cells per buffer
-constexpr int SGT = 128;                    // threads per group
+// Row pitches of the three row-sum buffers in float2 cells.  Each is 16*odd bytes modulo 128, so the LDS.128 of eight
+// consecutive rows (phase B: lane = row) hit eight different 16-byte bank groups.  Y3 is kept for all 84 cost columns,
+// Z9 for columns 6..77 and W21 for columns 8..75 (all that phase B reads).
+constexpr int SPY = 86, SPZ = 74, SPW = 70;
+constexpr int SZ0 = 6, SZ1 = 78, SW0 = 8, SW1 = 76;
+constexpr int SBUF = 32 * (SPY + SPZ + SPW);   // cells per group
+constexpr int SGT = 128;                       // threads per group
 constexpr float kKeep = 0.998f;             // candidate:  A' >= kKeep * running max        (eps  = 2e-3)
 constexpr float kClear = 1.005f;            // new max > kClear * old max clears the set    (eps' = 5e-3 >= eps/(1-eps))
 constexpr float kMinMax = 32768.0f * 144600.0f * 185910.0f;   // T
 
-__host__ __device__ inline size_t screen_smem_bytes(int L, int min_ds) {
-    return (size_t)2 * 3 * SBUF * sizeof(float2) + (size_t)SBR * (LW + make_pad_geom(64, 64, L, min_ds).rw) * 4;
+constexpr float kHVmax = 63.0f * 9.0f * 255.0f, kCmax = 81.0f * 9.0f * 255.0f;   // window sums of 255 per tap
+
+__host__ __device__ inline size_t screen_smem_bytes(int L, int min_ds, int groups) {
+    return (size_t)groups * SBUF * sizeof(float2) + (size_t)SBR * (LW + make_pad_geom(64, 64, L, min_ds).rw) * 4;
 }
 
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(SGT) : "memory"); }
@@ -58,71 +63,71 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a
 // Left band column of (cost column s, dx) = s+5+dx; right band column of (s, dx, level d) = s+dx+Lp-d
 // (same indexing as the cost phase of mbm_wta_fast.cu).  Lane .x = level d0, .y = level d0+1.
 __device__ __forceinline__ void screen_phase_a(const float *__restrict__ pl, const float *__restrict__ pr, int RW,
-                                               float2 *__restrict__ bY, float2 *__restrict__ bZ, float2 *__restrict__ bW) {
+                                               float2 *__restrict__ bY, float2 *__restrict__ bZ, float2 *__restrict__ bW,
+                                               bool keep_z, bool keep_w) {
     // Software pipeline with one dependent operation per stage: iteration `it` runs stage E_k on band row it-k-1, and
     // the stages are listed last-first, so every instruction of an iteration only reads results of EARLIER
     // iterations (the loop is fully unrolled: all ring indices are compile-time, rings are just names).  Pair sums
     // (p, q, zb, wb) are formed as soon as their operands exist, which leaves one dependent add per stage:
-    //   E0 loads | E1 a = l-r | E2 t = 255-|a| | E3 u = t0+t1 | E4 h3 = u+t2 | E5 X | E6 Y3 | E7 Z9 | E8 W21
-    //   X(R)   = h3(R) + h3(R+1) + h3(R+2)              3x3 cost of plane row R (band rows R..R+2)
+    //   E0 loads | E1 a = l-r | E3 u = |a0|+|a1| | E4 h3 = u+|a2| | E5 X | E6 Y3 | E7 Z9 | E8 W21
+    // The screen sums DISSIMILARITIES |l-r| (the abs is a free operand modifier) and phase B turns the window sums
+    // into similarities: N*255 - sum|a| differs from the sum of the reference's taps fl(255-|a|) by at most N*255*u.
+    //   X(R)   = h3(R) + h3(R+1) + h3(R+2)              3x3 sum of plane row R (band rows R..R+2)
     //   Y3(c)  = X(c-1) + X(c) + X(c+1)      c in [1,50]
     //   Z9(c)  = Y3(c-3) + Y3(c) + Y3(c+3)   c in [4,47]
     //   W21(c) = Z9(c-6) + Y3(c) + Z9(c+6)   c in [10,41]   (the 32 output rows of the tile are plane rows 10..41)
     float rw[4][7];          // raw band values: l0 l1 l2 | q0 q1 q2 q3
     float a[4][6];           // l - r per (tap column, level)
-    float2 t[4][3], u[4], h3[4], p[4], X[4], q[4];
+    float2 u[4], h3[4], p[4], X[4], q[4];
     float2 Y[16], Z[16], zb[16], wb[16];
 #pragma unroll
-    for (int it = 0; it < SBR + 10; it++) {
+    for (int it = 0; it < SBR + 9; it++) {
         {   // E8: row i delivered Z9(i-6) in the previous iteration -> W21(i-12)
-            const int i = it - 9, cz = i - 6, cw = cz - 6;
-            if (i >= 0 && i < SBR && cw >= 10 && cw <= 41) bW[(cw - 10) * SPITCH] = add2(wb[cw % 16], Z[cz % 16]);
+            const int i = it - 8, cz = i - 6, cw = cz - 6;
+            if (i >= 0 && i < SBR && cw >= 10 && cw <= 41 && keep_w) bW[(cw - 10) * SPW] = add2(wb[cw % 16], Z[cz % 16]);
         }
         {   // E7: row i delivered Y3(i-3) in the previous iteration
-            const int i = it - 8, cy = i - 3;
+            const int i = it - 7, cy = i - 3;
             if (i >= 0 && i < SBR && cy >= 1) {
                 if (cy >= 7) {
                     const int cz = cy - 3;
                     Z[cz % 16] = add2(zb[cz % 16], Y[cy % 16]);
-                    if (cz >= 10 && cz <= 41) bZ[(cz - 10) * SPITCH] = Z[cz % 16];
+                    if (cz >= 10 && cz <= 41 && keep_z) bZ[(cz - 10) * SPZ] = Z[cz % 16];
                 }
                 if (cy >= 4) zb[cy % 16] = add2(Y[(cy - 3) % 16], Y[cy % 16]);
                 if (cy >= 10 && cy <= 41) wb[cy % 16] = add2(Z[(cy - 6) % 16], Y[cy % 16]);   // Z9(cy-6) is 3 iterations old
             }
         }
         {   // E6: row i delivered X(i-2) in the previous iteration
-            const int i = it - 7, R = i - 2;
+            const int i = it - 6, R = i - 2;
             if (i >= 0 && i < SBR && R >= 0) {
                 if (R >= 2) {
                     const int cy = R - 1;
                     Y[cy % 16] = add2(q[(R - 1) % 4], X[R % 4]);
-                    if (cy >= 10 && cy <= 41) bY[(cy - 10) * SPITCH] = Y[cy % 16];
+                    if (cy >= 10 && cy <= 41) bY[(cy - 10) * SPY] = Y[cy % 16];
                 }
                 if (R >= 1) q[R % 4] = add2(X[(R - 1) % 4], X[R % 4]);
             }
         }
         {   // E5: h3(i) is one iteration old
-            const int i = it - 6;
+            const int i = it - 5;
             if (i >= 0 && i < SBR) {
                 if (i >= 2) X[(i - 2) % 4] = add2(p[(i - 1) % 4], h3[i % 4]);
                 if (i >= 1) p[i % 4] = add2(h3[(i - 1) % 4], h3[i % 4]);
             }
         }
-        {   // E4
-            const int i = it - 5;
-            if (i >= 0 && i < SBR) h3[i % 4] = add2(u[i % 4], t[i % 4][2]);
+        {   // E4: lane .x = level d0, .y = level d0+1
+            const int i = it - 4;
+            if (i >= 0 && i < SBR) {
+                const float *aa = a[i % 4];
+                h3[i % 4] = make_float2(__fadd_rn(u[i % 4].x, fabsf(aa[4])), __fadd_rn(u[i % 4].y, fabsf(aa[5])));
+            }
         }
         {   // E3
-            const int i = it - 4;
-            if (i >= 0 && i < SBR) u[i % 4] = add2(t[i % 4][0], t[i % 4][1]);
-        }
-        {   // E2: taps, lane .x = level d0, .y = level d0+1 (device_functions.cuh:66-70: 255 - |l - r|)
             const int i = it - 3;
             if (i >= 0 && i < SBR) {
                 const float *aa = a[i % 4];
-#pragma unroll
-                for (int k = 0; k < 3; k++)
-                    t[i % 4][k] = make_float2(__fsub_rn(255.0f, fabsf(aa[2 * k])), __fsub_rn(255.0f, fabsf(aa[2 * k + 1])));
+                u[i % 4] = make_float2(__fadd_rn(fabsf(aa[0]), fabsf(aa[2])), __fadd_rn(fabsf(aa[1]), fabsf(aa[3])));
             }
         }
         {   // E1: the loads were issued two iterations ago
@@ -150,16 +155,17 @@ __device__ __forceinline__ void screen_phase_a(const float *__restrict__ pl, con
     }
 }
 
-__global__ void __launch_bounds__(2 * SGT, 1)
+template <int NG>
+__global__ void __launch_bounds__(NG * SGT, 1)
 mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const float *__restrict__ padr,
                   unsigned *__restrict__ pass_mask, unsigned long long *__restrict__ stats, int *__restrict__ tile_order,
                   int *__restrict__ bucket_count) {
     extern __shared__ float4 smem4[];
-    float2 *bufs = reinterpret_cast<float2 *>(smem4);                   // [2 groups][Y3, Z9, W21][32][SPITCH]
-    float *bandL = reinterpret_cast<float *>(bufs + 2 * 3 * SBUF);      // [SBR][LW]
+    float2 *bufs = reinterpret_cast<float2 *>(smem4);                   // [NG groups][Y3 | Z9 | W21]
+    float *bandL = reinterpret_cast<float *>(bufs + NG * SBUF);         // [SBR][LW]
     float *bandR = bandL + SBR * LW;                                    // [SBR][RW]
     __shared__ __align__(8) uint64_t band_bar;
-    __shared__ unsigned s_mask[2];
+    __shared__ unsigned s_mask[NG];
     __shared__ int s_all;
 
     const int tid = threadIdx.x, grp = tid >> 7, gt = tid & (SGT - 1);
@@ -170,9 +176,9 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
 
     if (tid == 0) {
         mbar_init(&band_bar, 1);
-        s_mask[0] = s_mask[1] = 0u;
         s_all = 0;
     }
+    if (tid < NG) s_mask[tid] = 0u;
     __syncthreads();
     if (tid < 32) {
         if (tid == 0) mbar_expect_tx(&band_bar, (unsigned)(SBR * (LW + RW) * 4));
@@ -185,9 +191,9 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
         }
     }
 
-    float2 *bY = bufs + grp * 3 * SBUF, *bZ = bY + SBUF, *bW = bZ + SBUF;
+    float2 *bY = bufs + grp * SBUF, *bZ = bY + 32 * SPY, *bW = bZ + 32 * SPZ;
     // phase-B ownership: pooled row `row` of the tile, columns 16*seg .. 16*seg+15 (a warp = one segment: its 32
-    // lanes read 32 different rows, conflict-free with SPITCH)
+    // lanes read 32 different rows, conflict-free with the pitches above)
     const int row = gt & 31, seg = gt >> 5;
     float rmax[16], lo[16];
     unsigned cand[16];
@@ -205,9 +211,11 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
             if (++spins > (1 << 24)) __trap();  // a lost transaction must not hang the GPU
     }
 
-    for (int m = grp; m < M; m += 2) {
+    for (int m = grp; m < M; m += NG) {
         const int d0 = 2 * m;
-        if (gt < SXW) screen_phase_a(bandL + gt + 4, bandR + gt + (Lp - d0 - 2), RW, bY + gt, bZ + gt, bW + gt);
+        if (gt < SXW)
+            screen_phase_a(bandL + gt + 4, bandR + gt + (Lp - d0 - 2), RW, bY + gt, bZ + (gt - SZ0), bW + (gt - SW0),
+                           gt >= SZ0 && gt < SZ1, gt >= SW0 && gt < SW1);
         group_sync(grp);
 
         // ---- phase B ---------------------------------------------------------------------------------------
@@ -216,8 +224,8 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
         // interleave.  Absolute error of a window sum <= (5 + 2*15) u S_max (see the header).
         const float2 neg1 = make_float2(-1.0f, -1.0f);
         float2 dh[16], dc[16], V[16];
-        {   // H = 21-column sum of Y3: cost columns y .. y+20 for tile column y
-            const float4 *pp = reinterpret_cast<const float4 *>(bY + row * SPITCH + 16 * seg);
+        {   // H: 21-column sum of Y3, cost columns y .. y+20 for tile column y
+            const float4 *pp = reinterpret_cast<const float4 *>(bY + row * SPY + 16 * seg);
             float2 y[36];
 #pragma unroll
             for (int j = 0; j < 18; j++) {
@@ -234,8 +242,8 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
 #pragma unroll
             for (int k = 1; k < 16; k++) dh[k] = __ffma2_rn(y[k - 1], neg1, y[k + 20]);   // y[k+20] - y[k-1], one rounding
         }
-        {   // C = 9-column sum of Z9: cost columns y+6 .. y+14
-            const float4 *pp = reinterpret_cast<const float4 *>(bZ + row * SPITCH + 16 * seg + 6);
+        {   // C: 9-column sum of Z9, cost columns y+6 .. y+14 (buffer column = cost column - 6)
+            const float4 *pp = reinterpret_cast<const float4 *>(bZ + row * SPZ + 16 * seg);
             float2 z[24];
 #pragma unroll
             for (int j = 0; j < 12; j++) {
@@ -247,8 +255,9 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
 #pragma unroll
             for (int k = 1; k < 16; k++) dc[k] = __ffma2_rn(z[k - 1], neg1, z[k + 8]);
         }
-        {   // V = W21[y+9] + W21[y+10] + W21[y+11]
-            const float4 *pp = reinterpret_cast<const float4 *>(bW + row * SPITCH + 16 * seg + 8);
+        {   // V: W21 of cost columns y+9, y+10, y+11 (buffer column = cost column - 8); as a similarity
+            const float4 *pp = reinterpret_cast<const float4 *>(bW + row * SPW + 16 * seg);
+            const float2 vmax = make_float2(kHVmax, kHVmax);
             float2 w[20];
 #pragma unroll
             for (int j = 0; j < 10; j++) {
@@ -257,22 +266,24 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
                 w[2 * j + 1] = hi2(v4);
             }
 #pragma unroll
-            for (int k = 0; k < 16; k++) V[k] = add2(add2(w[k + 1], w[k + 2]), w[k + 3]);
+            for (int k = 0; k < 16; k++) V[k] = __ffma2_rn(add2(add2(w[k + 1], w[k + 2]), w[k + 3]), neg1, vmax);
         }
         float2 A[16];
-        {
+        {   // similarity sums = 255 * taps - dissimilarity sums; A' = (H' V') C'
+            const float2 hmax = make_float2(kHVmax, kHVmax), cmax = make_float2(kCmax, kCmax);
             float2 h = dh[0], c = dc[0];
-            A[0] = __fmul2_rn(__fmul2_rn(h, V[0]), c);
 #pragma unroll
-            for (int k = 1; k < 16; k++) {
-                h = add2(h, dh[k]);
-                c = add2(c, dc[k]);
-                A[k] = __fmul2_rn(__fmul2_rn(h, V[k]), c);
+            for (int k = 0; k < 16; k++) {
+                if (k) {
+                    h = add2(h, dh[k]);
+                    c = add2(c, dc[k]);
+                }
+                A[k] = __fmul2_rn(__fmul2_rn(__ffma2_rn(h, neg1, hmax), V[k]), __ffma2_rn(c, neg1, cmax));
             }
         }
         // ---- candidate bookkeeping: the set always contains every level pair within kKeep of the final maximum
         const bool has2 = (d0 + 1 < L);
-        const unsigned bit = 1u << (m >> 1);
+        const unsigned bit = 1u << (m / NG);
         float v[16];
         bool hit = false;
 #pragma unroll
@@ -296,9 +307,9 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
         group_sync(grp);   // the buffers are free for the next pass of this group
     }
 
-    // ---- merge the two groups' candidate sets (they screened disjoint level pairs) --------------------------------
+    // ---- merge the groups' candidate sets (they screened disjoint level pairs) -------------------------------------
     __syncthreads();
-    float *xm = reinterpret_cast<float *>(bufs);   // [2][32*64] running maxima, aliases the (now idle) buffers
+    float *xm = reinterpret_cast<float *>(bufs);   // [NG][32*64] running maxima, aliases the (now idle) buffers
 #pragma unroll
     for (int k = 0; k < 16; k++) xm[grp * 2048 + row * 64 + 16 * seg + k] = rmax[k];
     __syncthreads();
@@ -308,9 +319,16 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
     for (int k = 0; k < 16; k++) {
         const bool valid = (r0 + row < Hd) && (c0 + 16 * seg + k < Wd);
         if (!valid) continue;
-        const float other = xm[(grp ^ 1) * 2048 + row * 64 + 16 * seg + k];
+        float other = 0.0f;
+        bool nan = false;
+#pragma unroll
+        for (int og = 0; og < NG; og++) {
+            const float v = xm[og * 2048 + row * 64 + 16 * seg + k];
+            nan |= (v != v);
+            if (og != grp) other = fmaxf(other, v);
+        }
         if (!(other > rmax[k] * kClear)) mine |= cand[k];   // else: none of this group's pairs is within eps of the max
-        if (!(fmaxf(other, rmax[k]) >= kMinMax)) weak = true;   // bound not applicable (also catches NaN)
+        if (nan || !(fmaxf(other, rmax[k]) >= kMinMax)) weak = true;   // the bound does not apply to this pixel
     }
     mine = __reduce_or_sync(0xffffffffu, mine);
     weak = __any_sync(0xffffffffu, weak);
@@ -325,7 +343,7 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
             for (int m = 0; m < M; m++) w[m >> 5] |= 1u << (m & 31);
         } else {
             for (int m = 0; m < M; m++) {
-                if (!((s_mask[m & 1] >> (m >> 1)) & 1u)) continue;
+                if (!((s_mask[m % NG] >> (m / NG)) & 1u)) continue;
                 const int a = (m + M - 1) % M, b = (m + 1) % M;   // circular dilation by one pair
                 w[m >> 5] |= 1u << (m & 31);
                 w[a >> 5] |= 1u << (a & 31);
@@ -346,25 +364,32 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
     }
 }
 
-}  // namespace
-
-bool mbm_screen_supported(const Geom &g) {
-    const int Lp = (g.L + 1) & ~1;
-    return mbm_wta_fast_supported(g) && Lp / 2 <= 64 && Lp / 2 >= 2 && screen_smem_bytes(g.L, g.min_ds) <= 227 * 1024;
-}
-
-cudaError_t launch_mbm_screen(const Geom &g, int frames, const Scratch &s, cudaStream_t st) {
-    if (!mbm_screen_supported(g) || !s.padl || !s.padr || !s.pass_mask || !s.tile_order || !s.bucket_count) return cudaErrorNotSupported;
-    const size_t smem = screen_smem_bytes(g.L, g.min_ds);
+template <int NG>
+cudaError_t launch_screen_t(const Geom &g, int frames, const Scratch &s, cudaStream_t st) {
+    const size_t smem = screen_smem_bytes(g.L, g.min_ds, NG);
     const PadGeom pg = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
-    cudaError_t e = cudaFuncSetAttribute(mbm_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mbm_screen_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(pg.tiles_x, pg.tiles_y, frames);
     e = cudaMemsetAsync(s.bucket_count, 0, kScreenBuckets * sizeof(int), st);
     if (e != cudaSuccess) return e;
-    mbm_screen_kernel<<<grid, 2 * SGT, smem, st>>>(g, pg, s.padl, s.padr, s.pass_mask, s.screen_stats, s.tile_order,
-                                                   s.bucket_count);
+    mbm_screen_kernel<NG><<<grid, NG * SGT, smem, st>>>(g, pg, s.padl, s.padr, s.pass_mask, s.screen_stats, s.tile_order,
+                                                       s.bucket_count);
     return cudaGetLastError();
+}
+
+}  // namespace
+
+bool mbm_screen_supported(const Geom &g) {
+    const int Lp = (g.L + 1) & ~1;
+    return mbm_wta_fast_supported(g) && Lp / 2 <= 64 && Lp / 2 >= 2 && screen_smem_bytes(g.L, g.min_ds, 2) <= 227 * 1024;
+}
+
+cudaError_t launch_mbm_screen(const Geom &g, int frames, const Scratch &s, cudaStream_t st) {
+    if (!mbm_screen_supported(g) || !s.padl || !s.padr || !s.pass_mask || !s.tile_order || !s.bucket_count) return cudaErrorNotSupported;
+    // three groups (12 warps) when their buffers fit next to the row bands, else two
+    if (screen_smem_bytes(g.L, g.min_ds, 3) + 1024 <= 227 * 1024) return launch_screen_t<3>(g, frames, s, st);
+    return launch_screen_t<2>(g, frames, s, st);
 }
 
 }  // namespace sd

@@ -474,20 +474,14 @@ bool mbm_wta_fast_supported(const Geom &g) {
     return g.r_cost == 1 && g.rs == 1 && g.rm == 4 && g.rl == 10 && g.L >= 1 && smem_bytes<32>(g.L, g.min_ds) <= 227 * 1024;
 }
 
+// The wrap-padded planes (launch_pad_pooled) and, with use_screen, the pass masks of this chunk (launch_mbm_screen)
+// must already be in flight on `st`.
 cudaError_t launch_mbm_wta_fast(const Geom &g, int frames, const Scratch &s, float *dbg_cost, float *dbg_agg,
                                 cudaStream_t st, bool use_screen) {
     if (!mbm_wta_fast_supported(g) || !s.padl || !s.padr) return cudaErrorNotSupported;
-    {
-        cudaError_t e = launch_pad_pooled(g, frames, s, st);
-        if (e != cudaSuccess) return e;
-    }
     // the debug / reference-compat modes need every level of the volume: no screen there
     if (dbg_cost || dbg_agg) return launch_t<32, true, 0, true>(g, frames, s, dbg_cost, dbg_agg, st);
     if (s.agg_vol) return launch_t<32, false, 2, true>(g, frames, s, nullptr, nullptr, st);
-    if (use_screen) {
-        cudaError_t e = launch_mbm_screen(g, frames, s, st);
-        if (e != cudaSuccess) return e;
-    }
     switch (fast_mode()) {
         case 1: return launch_t<32, false, 1, false>(g, frames, s, nullptr, nullptr, st, use_screen);
         case 2: return launch_t<32, false, 2, false>(g, frames, s, nullptr, nullptr, st, use_screen);

@@ -179,6 +179,9 @@ class StereoMatching:
         """{kernel: (milliseconds, launches)} accumulated since the last read (device time, CUDA events)."""
         return self._handle.profile_read()
 
+    def profile_read_detail(self):
+        return self._handle.profile_read_detail()
+
     def launches_per_call(self, n_frames=1):
         return self._handle.launches_per_call(n_frames)
 
