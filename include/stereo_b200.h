@@ -139,6 +139,9 @@ int sd_set_variant(sd_handle *h, int variant);
 int sd_set_screen(sd_handle *h, int on);
 int sd_screen_active(sd_handle *h);
 int sd_screen_stats(sd_handle *h, double *evaluated_fraction, int reset);
+/* Adaptive policy: when a chunk's screen left more than 70 % of the level pairs to evaluate (flat or periodic scenes),
+ * the screen is skipped for the next 32 chunks and then probed again.  Returns the chunks left in the current pause. */
+int sd_screen_paused(sd_handle *h);
 
 /* Number of kernels one sd_compute call launches for n_frames frames. */
 int sd_launches_per_call(sd_handle *h, int n_frames);

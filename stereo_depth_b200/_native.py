@@ -19,7 +19,7 @@ CONFIG_FIELDS = ("height", "width", "downscale_factor", "min_disparity", "max_di
 # every symbol include/stereo_b200.h declares
 EXPORTS = ("sd_abi_version", "sd_config_default", "sd_dims", "sd_create", "sd_destroy", "sd_compute",
            "sd_compute_range", "sd_set_band", "sd_compute_host", "sd_get_stage", "sd_set_debug_volumes", "sd_set_compat", "sd_set_variant",
-           "sd_launches_per_call", "sd_frames_per_launch", "sd_active_variant", "sd_set_screen", "sd_screen_active", "sd_screen_stats", "sd_profile_enable", "sd_profile_read", "sd_profile_read_detail", "sd_metrics", "sd_point_cloud",
+           "sd_launches_per_call", "sd_frames_per_launch", "sd_active_variant", "sd_set_screen", "sd_screen_active", "sd_screen_stats", "sd_screen_paused", "sd_profile_enable", "sd_profile_read", "sd_profile_read_detail", "sd_metrics", "sd_point_cloud",
            "sd_last_error", "sd_last_cuda_error")
 
 
@@ -68,6 +68,7 @@ def lib():
     L.sd_set_screen.argtypes = [vp, ip]
     L.sd_screen_active.argtypes = [vp]
     L.sd_screen_stats.argtypes = [vp, C.POINTER(C.c_double), ip]
+    L.sd_screen_paused.argtypes = [vp]
     L.sd_profile_enable.argtypes = [vp, ip]
     L.sd_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.sd_profile_read_detail.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
@@ -145,6 +146,10 @@ class Handle:
     @property
     def screen_active(self):
         return bool(lib().sd_screen_active(self._h))
+
+    @property
+    def screen_paused(self):
+        return lib().sd_screen_paused(self._h)
 
     def screen_stats(self, reset=True):
         """Fraction of level pairs the fused kernel evaluated since the last reset (1.0 without the screen)."""

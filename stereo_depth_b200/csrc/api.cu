@@ -13,6 +13,8 @@ using namespace sd;
 
 namespace {
 constexpr int kSlots = 4;  // host pipeline depth (H2D / compute / D2H in flight)
+constexpr double kScreenGiveUp = 0.70;  // evaluated fraction above which the screen costs more than it saves
+constexpr int kScreenPause = 32;        // chunks without the screen before it is probed again
 constexpr int kProfMarks = 7;  // start | gray+pool | plane padding | level screen | cost+agg+WTA | secondary | fill
 }
 
@@ -25,6 +27,14 @@ struct sd_handle {
     bool auto_ws;    // variant 0 picks the warp-specialised schedule for this shape (sd_create's cost model)
     bool screen;     // certified level screen in front of the specialised kernel (default on where supported)
     int epoch;       // chunk counter, tags the out-of-range flag of the screen
+    // Adaptive policy: the screen only pays off when it removes work.  After every screened chunk the device counters
+    // {pairs flagged, pairs screened} are copied to pinned host memory (asynchronously; the host never waits for them)
+    // and the next chunks look at the latest pair that has arrived: if the fused kernel still had to evaluate more
+    // than kScreenGiveUp of the level pairs, the screen is skipped for kScreenPause chunks and then probed again.
+    // Results never depend on this -- the screen only changes the run time.
+    unsigned long long *stats_host;   // pinned [2]
+    unsigned long long stats_seen[2];
+    int screen_pause;
     Scratch s;
     float *dbg_cost, *dbg_agg;
     const float *gl_glob;  // band mode: left gray of the global image (device), else NULL
@@ -160,10 +170,27 @@ int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int 
         // (reference-compat mode: the kernels also materialise the aggregated volume into h->s.agg_vol)
         h->s.range_epoch = ++h->epoch;
         const int v = active_variant(h);
-        const bool screen = (v == 2) && screen_active(h);
+        bool screen = (v == 2) && screen_active(h);
+        if (screen && h->stats_host) {
+            // progress of the counters since the last look (whatever has arrived; possibly several chunks old)
+            const unsigned long long f = h->stats_host[0], n = h->stats_host[1];
+            if (n > h->stats_seen[1] && f >= h->stats_seen[0] && f - h->stats_seen[0] <= n - h->stats_seen[1]) {
+                if ((double)(f - h->stats_seen[0]) > kScreenGiveUp * (double)(n - h->stats_seen[1])) h->screen_pause = kScreenPause;
+                h->stats_seen[0] = f;
+                h->stats_seen[1] = n;
+            }
+            if (h->screen_pause > 0) {
+                h->screen_pause--;
+                screen = false;
+            }
+        }
         if (v == 2) SD_CUDA(h, launch_pad_pooled(h->g, frames, h->s, st));
         if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
-        if (screen) SD_CUDA(h, launch_mbm_screen(h->g, frames, h->s, st));
+        if (screen) {
+            SD_CUDA(h, launch_mbm_screen(h->g, frames, h->s, st));
+            if (h->stats_host)
+                SD_CUDA(h, cudaMemcpyAsync(h->stats_host, h->s.screen_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        }
         if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
         if (v == 3) SD_CUDA(h, launch_mbm_wta_ws(h->g, frames, h->s, st));   // (pads its planes itself)
         else if (v == 2) SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st, screen));
@@ -328,6 +355,8 @@ int sd_create(const sd_config *cfg, int device, int frames_per_launch, sd_handle
             SD_CUDA(h, cudaMalloc((void **)&h->s.bucket_count, kScreenBuckets * sizeof(int)));
             SD_CUDA(h, cudaMalloc((void **)&h->s.screen_stats, 2 * sizeof(unsigned long long)));
             SD_CUDA(h, cudaMemset(h->s.screen_stats, 0, 2 * sizeof(unsigned long long)));
+            SD_CUDA(h, cudaHostAlloc((void **)&h->stats_host, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+            h->stats_host[0] = h->stats_host[1] = 0;
             h->screen = true;
         }
     }
@@ -366,6 +395,7 @@ int sd_destroy(sd_handle *h) {
         cudaFree(h->s.agg_vol);
         cudaFree(h->s.padl);
         cudaFree(h->s.padr);
+        if (h->stats_host) cudaFreeHost(h->stats_host);
         cudaFree(h->s.pass_mask);
         cudaFree(h->s.tile_order);
         cudaFree(h->s.bucket_count);
@@ -560,8 +590,11 @@ int sd_set_screen(sd_handle *h, int on) {
     if (on && !h->s.pass_mask)
         return fail(h, SD_ERR_UNSUPPORTED, "the level screen needs the specialised fused kernel (radii 1/4/10, cost radius 1) and 3 <= L <= 128");
     h->screen = on != 0;
+    h->screen_pause = 0;
     return SD_OK;
 }
+
+int sd_screen_paused(sd_handle *h) { return h ? h->screen_pause : 0; }
 
 int sd_screen_active(sd_handle *h) { return (h && active_variant(h) == 2 && screen_active(h)) ? 1 : 0; }
 
@@ -575,7 +608,12 @@ int sd_screen_stats(sd_handle *h, double *evaluated_fraction, int reset) {
     if (h->ev_last_valid) SD_CUDA(h, cudaEventSynchronize(h->ev_last));
     SD_CUDA(h, cudaMemcpy(st, h->s.screen_stats, sizeof(st), cudaMemcpyDeviceToHost));
     if (st[1] > 0) *evaluated_fraction = (double)st[0] / (double)st[1];
-    if (reset) SD_CUDA(h, cudaMemset(h->s.screen_stats, 0, sizeof(st)));
+    if (reset) {
+        SD_CUDA(h, cudaDeviceSynchronize());   // no copy of the old counters may still be in flight
+        SD_CUDA(h, cudaMemset(h->s.screen_stats, 0, sizeof(st)));
+        if (h->stats_host) h->stats_host[0] = h->stats_host[1] = 0;
+        h->stats_seen[0] = h->stats_seen[1] = 0;
+    }
     return SD_OK;
 }
 

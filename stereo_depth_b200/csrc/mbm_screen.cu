@@ -76,18 +76,19 @@ __device__ __forceinline__ void screen_phase_a(const float *__restrict__ pl, con
     //   Y3(c)  = X(c-1) + X(c) + X(c+1)      c in [1,50]
     //   Z9(c)  = Y3(c-3) + Y3(c) + Y3(c+3)   c in [4,47]
     //   W21(c) = Z9(c-6) + Y3(c) + Z9(c+6)   c in [10,41]   (the 32 output rows of the tile are plane rows 10..41)
-    float rw[4][7];          // raw band values: l0 l1 l2 | q0 q1 q2 q3
+    constexpr int PF = 3;    // the band loads of a row are issued PF iterations before their first use
+    float rw[8][7];          // raw band values: l0 l1 l2 | q0 q1 q2 q3
     float a[4][6];           // l - r per (tap column, level)
     float2 u[4], h3[4], p[4], X[4], q[4];
     float2 Y[16], Z[16], zb[16], wb[16];
 #pragma unroll
-    for (int it = 0; it < SBR + 9; it++) {
+    for (int it = 0; it < SBR + PF + 7; it++) {
         {   // E8: row i delivered Z9(i-6) in the previous iteration -> W21(i-12)
-            const int i = it - 8, cz = i - 6, cw = cz - 6;
+            const int i = it - PF - 6, cz = i - 6, cw = cz - 6;
             if (i >= 0 && i < SBR && cw >= 10 && cw <= 41 && keep_w) bW[(cw - 10) * SPW] = add2(wb[cw % 16], Z[cz % 16]);
         }
         {   // E7: row i delivered Y3(i-3) in the previous iteration
-            const int i = it - 7, cy = i - 3;
+            const int i = it - PF - 5, cy = i - 3;
             if (i >= 0 && i < SBR && cy >= 1) {
                 if (cy >= 7) {
                     const int cz = cy - 3;
@@ -99,7 +100,7 @@ __device__ __forceinline__ void screen_phase_a(const float *__restrict__ pl, con
             }
         }
         {   // E6: row i delivered X(i-2) in the previous iteration
-            const int i = it - 6, R = i - 2;
+            const int i = it - PF - 4, R = i - 2;
             if (i >= 0 && i < SBR && R >= 0) {
                 if (R >= 2) {
                     const int cy = R - 1;
@@ -110,38 +111,38 @@ __device__ __forceinline__ void screen_phase_a(const float *__restrict__ pl, con
             }
         }
         {   // E5: h3(i) is one iteration old
-            const int i = it - 5;
+            const int i = it - PF - 3;
             if (i >= 0 && i < SBR) {
                 if (i >= 2) X[(i - 2) % 4] = add2(p[(i - 1) % 4], h3[i % 4]);
                 if (i >= 1) p[i % 4] = add2(h3[(i - 1) % 4], h3[i % 4]);
             }
         }
         {   // E4: lane .x = level d0, .y = level d0+1
-            const int i = it - 4;
+            const int i = it - PF - 2;
             if (i >= 0 && i < SBR) {
                 const float *aa = a[i % 4];
                 h3[i % 4] = make_float2(__fadd_rn(u[i % 4].x, fabsf(aa[4])), __fadd_rn(u[i % 4].y, fabsf(aa[5])));
             }
         }
         {   // E3
-            const int i = it - 3;
+            const int i = it - PF - 1;
             if (i >= 0 && i < SBR) {
                 const float *aa = a[i % 4];
                 u[i % 4] = make_float2(__fadd_rn(fabsf(aa[0]), fabsf(aa[2])), __fadd_rn(fabsf(aa[1]), fabsf(aa[3])));
             }
         }
-        {   // E1: the loads were issued two iterations ago
-            const int i = it - 2;
+        {   // E1: the loads were issued PF iterations ago
+            const int i = it - PF;
             if (i >= 0 && i < SBR) {
-                const float *w = rw[i % 4];
+                const float *w = rw[i % 8];
                 float *aa = a[i % 4];
                 aa[0] = __fsub_rn(w[0], w[4]); aa[1] = __fsub_rn(w[0], w[3]);
                 aa[2] = __fsub_rn(w[1], w[5]); aa[3] = __fsub_rn(w[1], w[4]);
                 aa[4] = __fsub_rn(w[2], w[6]); aa[5] = __fsub_rn(w[2], w[5]);
             }
         }
-        if (it < SBR) {   // E0 (volatile asm keeps the loads where they are written: two iterations ahead of their use)
-            float *w = rw[it % 4];
+        if (it < SBR) {   // E0 (volatile asm keeps the loads where they are written, PF iterations ahead of their use)
+            float *w = rw[it % 8];
             const unsigned la = smem_u32(pl + it * LW), ra = smem_u32(pr);
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w[0]) : "r"(la));
             asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(w[1]) : "r"(la));
@@ -309,9 +310,9 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
 
     // ---- merge the groups' candidate sets (they screened disjoint level pairs) -------------------------------------
     __syncthreads();
-    float *xm = reinterpret_cast<float *>(bufs);   // [NG][32*64] running maxima, aliases the (now idle) buffers
+    float *xm = reinterpret_cast<float *>(bufs);   // [NG][16][128] running maxima (lane-contiguous), aliases the idle buffers
 #pragma unroll
-    for (int k = 0; k < 16; k++) xm[grp * 2048 + row * 64 + 16 * seg + k] = rmax[k];
+    for (int k = 0; k < 16; k++) xm[grp * 2048 + k * SGT + gt] = rmax[k];
     __syncthreads();
     unsigned mine = 0u;
     bool weak = false;
@@ -323,7 +324,7 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
         bool nan = false;
 #pragma unroll
         for (int og = 0; og < NG; og++) {
-            const float v = xm[og * 2048 + row * 64 + 16 * seg + k];
+            const float v = xm[og * 2048 + k * SGT + gt];
             nan |= (v != v);
             if (og != grp) other = fmaxf(other, v);
         }

@@ -169,6 +169,11 @@ class StereoMatching:
     def screen_active(self):
         return self._handle.screen_active
 
+    @property
+    def screen_paused(self):
+        """Chunks left in the current pause of the adaptive screen policy (0 = screening)."""
+        return self._handle.screen_paused
+
     def screen_stats(self, reset=True):
         return self._handle.screen_stats(reset)
 

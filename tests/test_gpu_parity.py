@@ -154,6 +154,33 @@ def test_screened_matches_reference_fixtures(name):
     assert mismatch(got["out"], g["out_api"], (t["taint_out"] & 3) == 0) == 0
 
 
+def test_adaptive_screen_pauses_on_flat_scenes():
+    """A scene the screen cannot thin out (constant images: every level ties) makes the library skip the screen for
+    the following chunks; a textured scene keeps it on.  Results are identical either way."""
+    import torch
+    from stereo_depth_b200 import cuda_depth
+    H, W, n = 128, 192, 6
+    cfgobj = cuda_depth.StereoMatchingConfiguration(height=H, width=W, min_disparity=0, max_disparity=63)
+    flat = torch.full((n, 3, H, W), 90, dtype=torch.uint8, device="cuda")
+    sm = cuda_depth.StereoMatching(cfgobj, frames_per_launch=1)
+    assert sm.screen_active and sm.screen_paused == 0
+    out = sm.compute_disparity_batch(flat, flat).clone()
+    torch.cuda.synchronize()
+    sm.compute_disparity_batch(flat, flat)          # by now the first chunks' counters have arrived
+    assert sm.screen_paused > 0
+    assert torch.count_nonzero(out).item() == 0
+    ls, rs = zip(*[make_pair(H, W, 64, seed=21, frame=f)[:2] for f in range(n)])
+    L, R = torch.from_numpy(np.stack(ls)).cuda(), torch.from_numpy(np.stack(rs)).cuda()
+    sm2 = cuda_depth.StereoMatching(cfgobj, frames_per_launch=1)
+    a = sm2.compute_disparity_batch(L, R).clone()
+    torch.cuda.synchronize()
+    sm2.compute_disparity_batch(L, R)
+    assert sm2.screen_paused == 0
+    b = sm.compute_disparity_batch(L, R)            # same frames through the handle whose screen is paused
+    assert sm.screen_paused > 0
+    assert torch.equal(a, b)
+
+
 def test_generic_radii_vs_oracle():
     """Non-default radii go through the generic fused kernel."""
     kw = cfg_kw(80, 144, 2, 0, 23, ncc_patch_radius=2, sad_patch_radius=3, threshold=2,
