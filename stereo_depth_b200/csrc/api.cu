@@ -27,13 +27,13 @@ struct sd_handle {
     bool auto_ws;    // variant 0 picks the warp-specialised schedule for this shape (sd_create's cost model)
     bool screen;     // certified level screen in front of the specialised kernel (default on where supported)
     int epoch;       // chunk counter, tags the out-of-range flag of the screen
-    // Adaptive policy: the screen only pays off when it removes work.  After every screened chunk the device counters
-    // {pairs flagged, pairs screened} are copied to pinned host memory (asynchronously; the host never waits for them)
-    // and the next chunks look at the latest pair that has arrived: if the fused kernel still had to evaluate more
-    // than kScreenGiveUp of the level pairs, the screen is skipped for kScreenPause chunks and then probed again.
+    // Adaptive policy: the screen only pays off when it removes work.  The last block of every screen launch posts
+    // {chunk tag, pairs screened, pairs flagged} as one 64-bit store to mapped host memory (no copy, no wait); the
+    // next chunks look at the latest word that has arrived: if the fused kernel still had to evaluate more than
+    // kScreenGiveUp of the level pairs, the screen is skipped for kScreenPause chunks and then probed again.
     // Results never depend on this -- the screen only changes the run time.
-    unsigned long long *stats_host;   // pinned [2]
-    unsigned long long stats_seen[2];
+    unsigned long long *stats_host;   // mapped pinned word
+    unsigned long long stats_seen;
     int screen_pause;
     Scratch s;
     float *dbg_cost, *dbg_agg;
@@ -172,12 +172,11 @@ int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int 
         const int v = active_variant(h);
         bool screen = (v == 2) && screen_active(h);
         if (screen && h->stats_host) {
-            // progress of the counters since the last look (whatever has arrived; possibly several chunks old)
-            const unsigned long long f = h->stats_host[0], n = h->stats_host[1];
-            if (n > h->stats_seen[1] && f >= h->stats_seen[0] && f - h->stats_seen[0] <= n - h->stats_seen[1]) {
-                if ((double)(f - h->stats_seen[0]) > kScreenGiveUp * (double)(n - h->stats_seen[1])) h->screen_pause = kScreenPause;
-                h->stats_seen[0] = f;
-                h->stats_seen[1] = n;
+            const unsigned long long w = *(volatile unsigned long long *)h->stats_host;   // [tag:16][screened:24][flagged:24]
+            if (w != h->stats_seen) {
+                const double flagged = (double)(w & 0xffffffull), screened = (double)((w >> 24) & 0xffffffull);
+                if (screened > 0 && flagged > kScreenGiveUp * screened) h->screen_pause = kScreenPause;
+                h->stats_seen = w;
             }
             if (h->screen_pause > 0) {
                 h->screen_pause--;
@@ -186,11 +185,7 @@ int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int 
         }
         if (v == 2) SD_CUDA(h, launch_pad_pooled(h->g, frames, h->s, st));
         if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
-        if (screen) {
-            SD_CUDA(h, launch_mbm_screen(h->g, frames, h->s, st));
-            if (h->stats_host)
-                SD_CUDA(h, cudaMemcpyAsync(h->stats_host, h->s.screen_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        }
+        if (screen) SD_CUDA(h, launch_mbm_screen(h->g, frames, h->s, st));
         if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
         if (v == 3) SD_CUDA(h, launch_mbm_wta_ws(h->g, frames, h->s, st));   // (pads its planes itself)
         else if (v == 2) SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st, screen));
@@ -352,11 +347,12 @@ int sd_create(const sd_config *cfg, int device, int frames_per_launch, sd_handle
         if (mbm_screen_supported(g)) {
             SD_CUDA(h, cudaMalloc((void **)&h->s.pass_mask, F * (size_t)pg.tiles_x * pg.tiles_y * 4 * sizeof(unsigned)));
             SD_CUDA(h, cudaMalloc((void **)&h->s.tile_order, F * (size_t)pg.tiles_x * pg.tiles_y * kScreenBuckets * sizeof(int)));
-            SD_CUDA(h, cudaMalloc((void **)&h->s.bucket_count, kScreenBuckets * sizeof(int)));
+            SD_CUDA(h, cudaMalloc((void **)&h->s.bucket_count, kScreenCtrlInts * sizeof(int)));
             SD_CUDA(h, cudaMalloc((void **)&h->s.screen_stats, 2 * sizeof(unsigned long long)));
             SD_CUDA(h, cudaMemset(h->s.screen_stats, 0, 2 * sizeof(unsigned long long)));
-            SD_CUDA(h, cudaHostAlloc((void **)&h->stats_host, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
-            h->stats_host[0] = h->stats_host[1] = 0;
+            SD_CUDA(h, cudaHostAlloc((void **)&h->stats_host, sizeof(unsigned long long), cudaHostAllocMapped));
+            *h->stats_host = 0;
+            SD_CUDA(h, cudaHostGetDevicePointer((void **)&h->s.screen_host_word, h->stats_host, 0));
             h->screen = true;
         }
     }
@@ -608,12 +604,7 @@ int sd_screen_stats(sd_handle *h, double *evaluated_fraction, int reset) {
     if (h->ev_last_valid) SD_CUDA(h, cudaEventSynchronize(h->ev_last));
     SD_CUDA(h, cudaMemcpy(st, h->s.screen_stats, sizeof(st), cudaMemcpyDeviceToHost));
     if (st[1] > 0) *evaluated_fraction = (double)st[0] / (double)st[1];
-    if (reset) {
-        SD_CUDA(h, cudaDeviceSynchronize());   // no copy of the old counters may still be in flight
-        SD_CUDA(h, cudaMemset(h->s.screen_stats, 0, sizeof(st)));
-        if (h->stats_host) h->stats_host[0] = h->stats_host[1] = 0;
-        h->stats_seen[0] = h->stats_seen[1] = 0;
-    }
+    if (reset) SD_CUDA(h, cudaMemset(h->s.screen_stats, 0, sizeof(st)));
     return SD_OK;
 }
 

@@ -56,6 +56,7 @@ constexpr int kTileH = 32, kTileW = 64;   // pixels per tile of the specialised 
 constexpr int kBandRows = 56;             // band rows staged per tile (54 used + 2 only dead work items touch)
 constexpr int kBandLW = 96;               // left band pitch in shared memory (floats)
 constexpr int kScreenBuckets = 8;         // cost classes of the screened tiles (mbm_screen.cu -> mbm_wta_fast.cu)
+constexpr int kScreenCtrlInts = 16;       // bucket counts [8] | per-chunk pair accumulator (u64) | finished-block counter | pad
 struct PadGeom {
     int tiles_x, tiles_y, rows, pwl, pwr, rw, shift_r;
 };
@@ -93,7 +94,8 @@ struct Scratch {
     // Certified level screen (mbm_screen.cu), all NULL when unsupported:
     unsigned *pass_mask;              // [F][tiles_y][tiles_x][4] bit m = the fused kernel must run level pair m of that tile
     int *tile_order;                  // [kScreenBuckets][F*tiles] tile ids bucketed by flagged-pair count (heaviest bucket last)
-    int *bucket_count;                // [kScreenBuckets] tiles per bucket (zeroed before every screen launch)
+    int *bucket_count;                // [kScreenCtrlInts] tiles per bucket + per-chunk counters (zeroed before every screen launch)
+    unsigned long long *screen_host_word;  // device alias of a mapped host word: per-chunk screen outcome, or NULL
     unsigned long long *screen_stats; // [2] {level pairs flagged, level pairs screened} since the last reset
     int *range_flag;                  // == range_epoch when some pooled value of the current chunk lies outside [0,255]
     int range_epoch;                  // (or is NaN): the screen's error bound does not hold, masks are ignored

@@ -160,7 +160,7 @@ template <int NG>
 __global__ void __launch_bounds__(NG * SGT, 1)
 mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const float *__restrict__ padr,
                   unsigned *__restrict__ pass_mask, unsigned long long *__restrict__ stats, int *__restrict__ tile_order,
-                  int *__restrict__ bucket_count) {
+                  int *__restrict__ bucket_count, unsigned long long *__restrict__ host_word, int epoch) {
     extern __shared__ float4 smem4[];
     float2 *bufs = reinterpret_cast<float2 *>(smem4);                   // [NG groups][Y3 | Z9 | W21]
     float *bandL = reinterpret_cast<float *>(bufs + NG * SBUF);         // [SBR][LW]
@@ -362,6 +362,20 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
             atomicAdd(&stats[0], (unsigned long long)pc);
             atomicAdd(&stats[1], (unsigned long long)M);
         }
+        if (host_word) {
+            // Adaptive policy feed (api.cu): the last block of the launch posts {chunk tag, pairs screened, pairs
+            // flagged} of THIS chunk as one 64-bit store to mapped host memory; the host polls it, never waits.
+            unsigned long long *acc = reinterpret_cast<unsigned long long *>(bucket_count + kScreenBuckets);
+            int *done = bucket_count + kScreenBuckets + 2;
+            atomicAdd(acc, ((unsigned long long)M << 24) | (unsigned long long)pc);
+            __threadfence();
+            const int total = gridDim.x * gridDim.y * gridDim.z;
+            if (atomicAdd(done, 1) == total - 1) {
+                __threadfence();
+                const unsigned long long v = atomicAdd(acc, 0ull);
+                *reinterpret_cast<volatile unsigned long long *>(host_word) = ((unsigned long long)(epoch & 0xffff) << 48) | (v & 0xffffffffffffull);
+            }
+        }
     }
 }
 
@@ -372,10 +386,10 @@ cudaError_t launch_screen_t(const Geom &g, int frames, const Scratch &s, cudaStr
     cudaError_t e = cudaFuncSetAttribute(mbm_screen_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(pg.tiles_x, pg.tiles_y, frames);
-    e = cudaMemsetAsync(s.bucket_count, 0, kScreenBuckets * sizeof(int), st);
+    e = cudaMemsetAsync(s.bucket_count, 0, kScreenCtrlInts * sizeof(int), st);
     if (e != cudaSuccess) return e;
     mbm_screen_kernel<NG><<<grid, NG * SGT, smem, st>>>(g, pg, s.padl, s.padr, s.pass_mask, s.screen_stats, s.tile_order,
-                                                       s.bucket_count);
+                                                       s.bucket_count, s.screen_host_word, s.range_epoch);
     return cudaGetLastError();
 }
 

@@ -159,8 +159,8 @@ def test_adaptive_screen_pauses_on_flat_scenes():
     the following chunks; a textured scene keeps it on.  Results are identical either way."""
     import torch
     from stereo_depth_b200 import cuda_depth
-    H, W, n = 128, 192, 6
-    cfgobj = cuda_depth.StereoMatchingConfiguration(height=H, width=W, min_disparity=0, max_disparity=63)
+    H, W, n = 256, 640, 4
+    cfgobj = cuda_depth.StereoMatchingConfiguration(height=H, width=W, min_disparity=0, max_disparity=127)
     flat = torch.full((n, 3, H, W), 90, dtype=torch.uint8, device="cuda")
     sm = cuda_depth.StereoMatching(cfgobj, frames_per_launch=1)
     assert sm.screen_active and sm.screen_paused == 0
@@ -169,7 +169,7 @@ def test_adaptive_screen_pauses_on_flat_scenes():
     sm.compute_disparity_batch(flat, flat)          # by now the first chunks' counters have arrived
     assert sm.screen_paused > 0
     assert torch.count_nonzero(out).item() == 0
-    ls, rs = zip(*[make_pair(H, W, 64, seed=21, frame=f)[:2] for f in range(n)])
+    ls, rs = zip(*[make_pair(H, W, 128, seed=21, frame=f)[:2] for f in range(n)])
     L, R = torch.from_numpy(np.stack(ls)).cuda(), torch.from_numpy(np.stack(rs)).cuda()
     sm2 = cuda_depth.StereoMatching(cfgobj, frames_per_launch=1)
     a = sm2.compute_disparity_batch(L, R).clone()

@@ -14,7 +14,11 @@ shutil.copy(os.path.join(G, "bench.json"), os.path.join(P, "r01_bench_c3_1gpu.js
 shutil.copy(os.path.join(G, "bench_reference.json"), os.path.join(P, "r01_bench_reference_c3.json"))
 with open(os.path.join(P, "r01_ncu_kernelB_summary.txt"), "w") as f:
     subprocess.run(["python", os.path.join(ROOT, "tools", "ncu_phase_report.py"), os.path.join(G, "prof_kernelB.ncu-rep")], stdout=f)
-for rep, out in (("prof_kernelB.ncu-rep", "r01_ncu_kernelB_details.txt"), ("prof_others.ncu-rep", "r01_ncu_other_kernels_details.txt")):
+for rep, out in (("prof_screen.ncu-rep", "r01_ncu_screen_summary.txt"), ("prof_kernelB_screened.ncu-rep", "r01_ncu_kernelB_screened_summary.txt")):
+    with open(os.path.join(P, out), "w") as f:
+        subprocess.run(["python", os.path.join(ROOT, "tools", "ncu_phase_report.py"), os.path.join(G, rep)], stdout=f)
+for rep, out in (("prof_kernelB.ncu-rep", "r01_ncu_kernelB_details.txt"), ("prof_others.ncu-rep", "r01_ncu_other_kernels_details.txt"),
+                 ("prof_screen.ncu-rep", "r01_ncu_screen_details.txt")):
     with open(os.path.join(P, out), "w") as f:
         subprocess.run(["ncu", "-i", os.path.join(G, rep), "--page", "details"], stdout=f, stderr=subprocess.DEVNULL)
 
@@ -57,7 +61,16 @@ def val(name):
 
 
 t = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
-json.dump({"C3_per_frame": t / 8, "note": "(dram__bytes_read.sum + dram__bytes_write.sum) / 8 of one mbm_wta_fast_kernel launch over 8 frames "
-           "of C3 (ncu --set full, profiles/r01_ncu_kernelB_summary.txt); bench.py scales it by the frames per launch"},
+ts = 0.0
+for rep in ("prof_screen.ncu-rep", "prof_kernelB_screened.ncu-rep"):
+    raw = subprocess.run(["ncu", "-i", os.path.join(G, rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, d = rows[0], rows[1], rows[2]
+    ts += val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
+json.dump({"C3_per_frame": t / 8, "C3_screened_per_frame": ts / 8,
+           "note": "(dram__bytes_read.sum + dram__bytes_write.sum) / 8 of one launch over 8 frames of C3 (ncu --set full): C3_per_frame = "
+                   "mbm_wta_fast_kernel evaluating all levels (profiles/r01_ncu_kernelB_summary.txt); C3_screened_per_frame = mbm_screen_kernel + "
+                   "mbm_wta_fast_kernel behind the screen (r01_ncu_screen_summary.txt, r01_ncu_kernelB_screened_summary.txt); bench.py scales it by "
+                   "the frames per launch"},
           open(os.path.join(P, "kernelB_traffic.json"), "w"))
-print("kernel B DRAM bytes per frame:", t / 8)
+print("kernel B DRAM bytes per frame:", t / 8, "screened:", ts / 8)

@@ -22,6 +22,8 @@ sm = cuda_depth.StereoMatching(cuda_depth.StereoMatchingConfiguration(height=H, 
                                frames_per_launch=2 * nrep)
 if os.environ.get("SD_VARIANT"):
     sm.set_variant(os.environ["SD_VARIANT"])
+if os.environ.get("SD_SCREEN") is not None and sm.screen_active:
+    sm.set_screen(os.environ["SD_SCREEN"] == "1")
 out = None
 for _ in range(reps):
     out = sm.compute_disparity_batch(l, r, out=out)
