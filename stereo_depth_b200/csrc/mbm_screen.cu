@@ -5,9 +5,9 @@
 // still BE the arg-max need that treatment.  This kernel computes every aggregated cost approximately -- the same
 // fp32 taps, summed separably (3x3 cost -> nested vertical 3/9/21-row sums -> sliding horizontal 21/9/3-column
 // sums; ~45 lane-ops per cell instead of 237) -- and keeps, per pixel, the set of level pairs whose approximate
-// cost is within a RIGOROUS error bound of the pixel's approximate maximum.  The union over a 32x64 tile, dilated
-// by one pair (the secondary matching reads A[d*-1], A[d*+1]; circular, secondary_matching.cu:28-31), is the
-// tile's pass mask: mbm_wta_fast_kernel then runs its exact passes only for those level pairs.  Results are
+// cost is within a RIGOROUS error bound of the pixel's approximate maximum.  The union over a 32x64 tile of those
+// levels and their two neighbours (the secondary matching reads A[d*-1], A[d*+1]; circular,
+// secondary_matching.cu:28-31), as level pairs, is the tile's pass mask: mbm_wta_fast_kernel then runs its exact passes only for those level pairs.  Results are
 // bit-identical to evaluating all levels (tests/test_gpu_parity.py runs both ways):
 //
 //   * taps  t = 255 - |l - r|  are computed exactly like the reference (device_functions.cuh:66-70), so both sides
@@ -156,7 +156,9 @@ __device__ __forceinline__ void screen_phase_a(const float *__restrict__ pl, con
     }
 }
 
-template <int NG>
+// MaskT: candidate set of one pixel, two bits per level pair screened by the thread's group (bit 2j = level 2m,
+// bit 2j+1 = level 2m+1 for the group's j-th pair m = j*NG + group): 32 bits hold 16 pairs per group, 64 bits 32.
+template <int NG, typename MaskT>
 __global__ void __launch_bounds__(NG * SGT, 1)
 mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const float *__restrict__ padr,
                   unsigned *__restrict__ pass_mask, unsigned long long *__restrict__ stats, int *__restrict__ tile_order,
@@ -166,7 +168,7 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
     float *bandL = reinterpret_cast<float *>(bufs + NG * SBUF);         // [SBR][LW]
     float *bandR = bandL + SBR * LW;                                    // [SBR][RW]
     __shared__ __align__(8) uint64_t band_bar;
-    __shared__ unsigned s_mask[NG];
+    __shared__ MaskT s_mask[NG];
     __shared__ int s_all;
 
     const int tid = threadIdx.x, grp = tid >> 7, gt = tid & (SGT - 1);
@@ -179,7 +181,7 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
         mbar_init(&band_bar, 1);
         s_all = 0;
     }
-    if (tid < NG) s_mask[tid] = 0u;
+    if (tid < NG) s_mask[tid] = 0;
     __syncthreads();
     if (tid < 32) {
         if (tid == 0) mbar_expect_tx(&band_bar, (unsigned)(SBR * (LW + RW) * 4));
@@ -197,13 +199,13 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
     // lanes read 32 different rows, conflict-free with the pitches above)
     const int row = gt & 31, seg = gt >> 5;
     float rmax[16], lo[16];
-    unsigned cand[16];
+    MaskT cand[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         const bool valid = (r0 + row < Hd) && (c0 + 16 * seg + k < Wd);
         rmax[k] = 0.0f;
         lo[k] = valid ? 0.0f : __int_as_float(0x7f800000);   // pixels outside the image never become candidates
-        cand[k] = 0u;
+        cand[k] = 0;
     }
 
     {
@@ -282,9 +284,9 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
                 A[k] = __fmul2_rn(__fmul2_rn(__ffma2_rn(h, neg1, hmax), V[k]), __ffma2_rn(c, neg1, cmax));
             }
         }
-        // ---- candidate bookkeeping: the set always contains every level pair within kKeep of the final maximum
+        // ---- candidate bookkeeping: the set always contains every LEVEL within kKeep of the final maximum -----------
         const bool has2 = (d0 + 1 < L);
-        const unsigned bit = 1u << (m / NG);
+        const MaskT bitx = (MaskT)1 << (2 * (m / NG)), bity = bitx << 1;
         float v[16];
         bool hit = false;
 #pragma unroll
@@ -296,12 +298,14 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 if (v[k] >= lo[k]) {
-                    if (v[k] > rmax[k] * kClear) cand[k] = 0u;   // everything seen so far is below (1-eps) of the new max
-                    cand[k] |= bit;
+                    if (v[k] > rmax[k] * kClear) cand[k] = 0;   // everything seen so far is below (1-eps) of the new max
                     if (v[k] > rmax[k]) {
                         rmax[k] = v[k];
                         lo[k] = v[k] * kKeep;
                     }
+                    // both levels against the UPDATED threshold (<= kKeep * final maximum: still a superset)
+                    if (A[k].x >= lo[k]) cand[k] |= bitx;
+                    if (has2 && A[k].y >= lo[k]) cand[k] |= bity;
                 }
             }
         }
@@ -314,7 +318,7 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
 #pragma unroll
     for (int k = 0; k < 16; k++) xm[grp * 2048 + k * SGT + gt] = rmax[k];
     __syncthreads();
-    unsigned mine = 0u;
+    MaskT mine = 0;
     bool weak = false;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
@@ -331,7 +335,11 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
         if (!(other > rmax[k] * kClear)) mine |= cand[k];   // else: none of this group's pairs is within eps of the max
         if (nan || !(fmaxf(other, rmax[k]) >= kMinMax)) weak = true;   // the bound does not apply to this pixel
     }
-    mine = __reduce_or_sync(0xffffffffu, mine);
+    if (sizeof(MaskT) == 8)
+        mine = (MaskT)(((unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)((unsigned long long)mine >> 32)) << 32) |
+                       __reduce_or_sync(0xffffffffu, (unsigned)mine));
+    else
+        mine = (MaskT)__reduce_or_sync(0xffffffffu, (unsigned)mine);
     weak = __any_sync(0xffffffffu, weak);
     if ((tid & 31) == 0) {
         if (mine) atomicOr(&s_mask[grp], mine);
@@ -343,9 +351,11 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
         if (s_all) {
             for (int m = 0; m < M; m++) w[m >> 5] |= 1u << (m & 31);
         } else {
-            for (int m = 0; m < M; m++) {
-                if (!((s_mask[m % NG] >> (m / NG)) & 1u)) continue;
-                const int a = (m + M - 1) % M, b = (m + 1) % M;   // circular dilation by one pair
+            // a candidate level d needs d-1, d, d+1 (circular in L, secondary_matching.cu:28-31) evaluated exactly
+            for (int d = 0; d < L; d++) {
+                const int m = d >> 1;
+                if (!((s_mask[m % NG] >> (2 * (m / NG) + (d & 1))) & 1)) continue;
+                const int a = ((d + L - 1) % L) >> 1, b = ((d + 1) % L) >> 1;
                 w[m >> 5] |= 1u << (m & 31);
                 w[a >> 5] |= 1u << (a & 31);
                 w[b >> 5] |= 1u << (b & 31);
@@ -379,16 +389,16 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
     }
 }
 
-template <int NG>
+template <int NG, typename MaskT>
 cudaError_t launch_screen_t(const Geom &g, int frames, const Scratch &s, cudaStream_t st) {
     const size_t smem = screen_smem_bytes(g.L, g.min_ds, NG);
     const PadGeom pg = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
-    cudaError_t e = cudaFuncSetAttribute(mbm_screen_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mbm_screen_kernel<NG, MaskT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(pg.tiles_x, pg.tiles_y, frames);
     e = cudaMemsetAsync(s.bucket_count, 0, kScreenCtrlInts * sizeof(int), st);
     if (e != cudaSuccess) return e;
-    mbm_screen_kernel<NG><<<grid, NG * SGT, smem, st>>>(g, pg, s.padl, s.padr, s.pass_mask, s.screen_stats, s.tile_order,
+    mbm_screen_kernel<NG, MaskT><<<grid, NG * SGT, smem, st>>>(g, pg, s.padl, s.padr, s.pass_mask, s.screen_stats, s.tile_order,
                                                        s.bucket_count, s.screen_host_word, s.range_epoch);
     return cudaGetLastError();
 }
@@ -402,9 +412,10 @@ bool mbm_screen_supported(const Geom &g) {
 
 cudaError_t launch_mbm_screen(const Geom &g, int frames, const Scratch &s, cudaStream_t st) {
     if (!mbm_screen_supported(g) || !s.padl || !s.padr || !s.pass_mask || !s.tile_order || !s.bucket_count) return cudaErrorNotSupported;
-    // three groups (12 warps) when their buffers fit next to the row bands, else two
-    if (screen_smem_bytes(g.L, g.min_ds, 3) + 1024 <= 227 * 1024) return launch_screen_t<3>(g, frames, s, st);
-    return launch_screen_t<2>(g, frames, s, st);
+    // three groups (12 warps) when their buffers fit next to the row bands and 16 pairs per group suffice, else two
+    const int M = ((g.L + 1) & ~1) / 2;
+    if (screen_smem_bytes(g.L, g.min_ds, 3) + 1024 <= 227 * 1024 && M <= 48) return launch_screen_t<3, unsigned>(g, frames, s, st);
+    return launch_screen_t<2, unsigned long long>(g, frames, s, st);
 }
 
 }  // namespace sd
