@@ -100,6 +100,20 @@ int sd_compute_range(sd_handle *h, const void *left, const void *right, int dtyp
  * `global_left_gray` ([global_height, W] floats, device).  global_height <= 0 switches back to normal mode. */
 int sd_set_band(sd_handle *h, int pooled_row_offset, int global_height, const float *global_left_gray);
 
+/* Row-band mode over PEER MEMORY (NVLink / NVSwitch), one process per GPU: the halo exchange and the left-gray exchange of
+ * sd_set_band's mode as kernels that store directly into the other ranks' HBM and signal with system-scope flags (no NCCL
+ * call, no host synchronisation on the data path).
+ *   sd_band_p2p_init     the handle must have been created with height = band rows + 2 * halo_rows.  band_row0[world+1]:
+ *                        first full-resolution row of every rank's band, band_row0[world] = global height.  Allocates the
+ *                        exported buffers and writes this rank's 64-byte CUDA IPC handle to ipc_handle_out.
+ *   sd_band_p2p_connect  ipc_handles: the world x 64 bytes of all ranks (exchanged by the caller, e.g. an all-gather).
+ *   sd_band_p2p_compute  left_band / right_band: [3, band rows, W] of `dtype` (device); out: [band rows + 2 * halo_rows, W]
+ *                        floats, rows halo_rows .. halo_rows + band rows - 1 are this rank's part of the disparity map.
+ * Every rank must call sd_band_p2p_compute the same number of times (a missing peer traps after ~10 s). */
+int sd_band_p2p_init(sd_handle *h, int world, int rank, const int32_t *band_row0, int halo_rows, int dtype, void *ipc_handle_out);
+int sd_band_p2p_connect(sd_handle *h, const void *ipc_handles);
+int sd_band_p2p_compute(sd_handle *h, const void *left_band, const void *right_band, float *out, void *cuda_stream);
+
 /* Same computation with HOST buffers (pinned memory recommended): host->device copies, the
  * kernels and device->host copies are pipelined over internal streams, chunk by chunk.
  * Synchronous: returns when `out` is complete.  This is the end-to-end call
@@ -135,6 +149,8 @@ int sd_set_variant(sd_handle *h, int variant);
  * reference's arg-max (rigorous fp32 error bound, stereo_depth_b200/csrc/mbm_screen.cu); the fused kernel then
  * evaluates the reference's sequential chains (multi_block_matching_cost_aggregation.cu:56-87) only for those.
  * Results are bit-identical with the screen on or off; only the run time changes (and becomes scene dependent).
+ * With variant 0 the screen is skipped for launches of less than about two waves of tiles (single small frames), where
+ * the heaviest tile bounds the launch time; sd_screen_active / sd_active_variant answer for a full chunk.
  * sd_screen_stats: fraction of level pairs the fused kernel had to evaluate since the last reset (synchronises). */
 int sd_set_screen(sd_handle *h, int on);
 int sd_screen_active(sd_handle *h);

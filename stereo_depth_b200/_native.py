@@ -18,7 +18,7 @@ CONFIG_FIELDS = ("height", "width", "downscale_factor", "min_disparity", "max_di
 
 # every symbol include/stereo_b200.h declares
 EXPORTS = ("sd_abi_version", "sd_config_default", "sd_dims", "sd_create", "sd_destroy", "sd_compute",
-           "sd_compute_range", "sd_set_band", "sd_compute_host", "sd_get_stage", "sd_set_debug_volumes", "sd_set_compat", "sd_set_variant",
+           "sd_compute_range", "sd_set_band", "sd_band_p2p_init", "sd_band_p2p_connect", "sd_band_p2p_compute", "sd_compute_host", "sd_get_stage", "sd_set_debug_volumes", "sd_set_compat", "sd_set_variant",
            "sd_launches_per_call", "sd_frames_per_launch", "sd_active_variant", "sd_set_screen", "sd_screen_active", "sd_screen_stats", "sd_screen_paused", "sd_profile_enable", "sd_profile_read", "sd_profile_read_detail", "sd_metrics", "sd_point_cloud",
            "sd_last_error", "sd_last_cuda_error")
 
@@ -58,6 +58,9 @@ def lib():
     L.sd_compute_host.argtypes = [vp, vp, vp, ip, ip, vp]
     L.sd_compute_range.argtypes = [vp, vp, vp, ip, ip, vp, vp, ip, ip]
     L.sd_set_band.argtypes = [vp, ip, ip, vp]
+    L.sd_band_p2p_init.argtypes = [vp, ip, ip, i32p, ip, ip, vp]
+    L.sd_band_p2p_connect.argtypes = [vp, vp]
+    L.sd_band_p2p_compute.argtypes = [vp, vp, vp, vp, vp]
     L.sd_get_stage.argtypes = [vp, ip, ip, vp, vp]
     L.sd_set_debug_volumes.argtypes = [vp, vp, vp]
     L.sd_set_variant.argtypes = [vp, ip]
@@ -124,6 +127,19 @@ class Handle:
 
     def set_band(self, pooled_row_offset, global_height, global_left_gray_ptr):
         self.check(lib().sd_set_band(self._h, pooled_row_offset, global_height, global_left_gray_ptr))
+
+    def band_p2p_init(self, world, rank, band_row0, halo_rows, dtype):
+        """Returns this rank's 64-byte CUDA IPC handle (bytes)."""
+        rows = (C.c_int32 * len(band_row0))(*band_row0)
+        buf = C.create_string_buffer(64)
+        self.check(lib().sd_band_p2p_init(self._h, world, rank, rows, halo_rows, dtype, buf))
+        return buf.raw
+
+    def band_p2p_connect(self, all_handles):
+        self.check(lib().sd_band_p2p_connect(self._h, C.c_char_p(all_handles)))
+
+    def band_p2p_compute(self, left_ptr, right_ptr, out_ptr, stream_ptr):
+        self.check(lib().sd_band_p2p_compute(self._h, left_ptr, right_ptr, out_ptr, stream_ptr))
 
     def compute_host(self, left_ptr, right_ptr, dtype, n_frames, out_ptr):
         self.check(lib().sd_compute_host(self._h, left_ptr, right_ptr, dtype, n_frames, out_ptr))

@@ -16,6 +16,11 @@ Two modes:
   kernel needs global knowledge (the reference's `x == 0` rule, the `(k+1)*x` colour row and the last-row rule),
   which it gets from `sd_set_band` plus an all-gather of the left gray bands (the second exchange step).
   Band results are bit-identical to the single-GPU result (tests/test_multi_gpu.py).
+
+  `BandedStereoMatching(..., p2p=True)` runs the same two exchange steps over PEER MEMORY instead of NCCL: the library
+  stores the halo rows straight into the neighbours' HBM while it copies the band into its own window, publishes its
+  left gray band for the other ranks' fill kernels to read in place, and synchronises with system-scope flags
+  (stereo_depth_b200/csrc/band_p2p.cu).  torch.distributed is then only used once, to exchange the CUDA IPC handles.
 """
 from dataclasses import dataclass
 
@@ -126,10 +131,12 @@ class BandedStereoMatching:
         full = sm.gather(out_band)                       # optional: [H, W] on every rank
     """
 
-    def __init__(self, configuration, group=None):
+    def __init__(self, configuration, group=None, p2p=False, variant=None):
         from . import _native as N
         self._N = N
         self.group = group
+        self.p2p = bool(p2p)
+        self._p2p_dtype = None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         g = configuration._as_struct()
@@ -140,6 +147,8 @@ class BandedStereoMatching:
         local.height = self.plan.local_rows
         self.device = torch.cuda.current_device()
         self.handle = N.Handle(local, self.device, 1)
+        if variant is not None:   # e.g. "fast" pins the screened two-phase kernel (auto decides per launch size)
+            self.handle.set_variant({"auto": 0, "generic": 1, "fast": 2, "ws": 3}.get(variant, variant))
         self.H, self.W = g.height, g.width
         self._out = torch.empty((self.plan.local_rows, self.W), dtype=torch.float32, device="cuda")
         self._gray = torch.empty((self.plan.local_rows, self.W), dtype=torch.float32, device="cuda")
@@ -153,6 +162,8 @@ class BandedStereoMatching:
         if left_band.dtype != right_band.dtype:
             raise RuntimeError("left and right bands must have the same dtype")
         code = N.SD_U8 if left_band.dtype == torch.uint8 else N.SD_F32
+        if self.p2p:
+            return self._compute_p2p(left_band, right_band, code)
         # exchange step 1: raw halo rows of both views in ONE ring send/recv over NVLink
         both = exchange_halos(torch.cat([left_band, right_band], dim=0), p.halo_rows, self.group)
         left, right = both[:3], both[3:]
@@ -170,6 +181,30 @@ class BandedStereoMatching:
             self._gl_glob = gather_rows(mine, self.rows_per_rank, self.group)
         self.handle.set_band(p.pooled_row_offset, self.H, self._gl_glob.data_ptr())
         self.handle.compute_range(None, None, code, 1, self._out.data_ptr(), stream, 1, 3)
+        return self._out[p.halo_rows:p.halo_rows + p.band_rows]
+
+    def _compute_p2p(self, left_band, right_band, code):
+        p = self.plan
+        if self._p2p_dtype is None:
+            K = p.K
+            row0 = [0]
+            for r in self.rows_per_rank:
+                row0.append(row0[-1] + r)
+            assert row0[self.rank] == p.x0 * K
+            mine = self.handle.band_p2p_init(self.world, self.rank, row0, p.halo_rows, code)
+            if self.world > 1:
+                t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).cuda()
+                allh = torch.empty(64 * self.world, dtype=torch.uint8, device="cuda")
+                dist.all_gather_into_tensor(allh, t, group=self.group)
+                self.handle.band_p2p_connect(bytes(allh.cpu().numpy().tobytes()))
+                dist.barrier(group=self.group)   # every rank has mapped every buffer before anyone stores into one
+            self._p2p_dtype = code
+        elif self._p2p_dtype != code:
+            raise RuntimeError("peer-memory band mode was initialised for the other input dtype")
+        if not (left_band.is_contiguous() and right_band.is_contiguous()):
+            raise RuntimeError("bands must be contiguous")
+        stream = torch.cuda.current_stream().cuda_stream
+        self.handle.band_p2p_compute(left_band.data_ptr(), right_band.data_ptr(), self._out.data_ptr(), stream)
         return self._out[p.halo_rows:p.halo_rows + p.band_rows]
 
     def gather(self, out_band):

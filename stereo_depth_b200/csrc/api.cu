@@ -25,6 +25,7 @@ struct sd_handle {
     int chunk;       // frames per launch
     int variant;     // 0 auto, 1 generic, 2 specialised, 3 warp-specialised
     bool auto_ws;    // variant 0 picks the warp-specialised schedule for this shape (sd_create's cost model)
+    int sms, per_sm_fast;  // SM count and resident blocks per SM of the specialised kernel (launch cost models)
     bool screen;     // certified level screen in front of the specialised kernel (default on where supported)
     int epoch;       // chunk counter, tags the out-of-range flag of the screen
     // Adaptive policy: the screen only pays off when it removes work.  The last block of every screen launch posts
@@ -37,7 +38,17 @@ struct sd_handle {
     int screen_pause;
     Scratch s;
     float *dbg_cost, *dbg_agg;
-    const float *gl_glob;  // band mode: left gray of the global image (device), else NULL
+    GrayView gv;     // band mode: where the left gray of the global image lives, else all zero
+    // peer-memory row bands (sd_band_p2p_*): one exported allocation per rank = [window L | window R | gray 0 | gray 1 | flags]
+    struct P2P {
+        bool on, connected;
+        int world, rank, dtype, halo_rows;
+        int row0[9];                 // full-resolution first row of every rank's band (+ total height)
+        size_t win_bytes, gray_bytes;  // per window / per published gray buffer (sized for the tallest band)
+        char *base;                  // my allocation
+        char *peer[8];               // every rank's allocation (peer[rank] == base)
+        unsigned epoch;
+    } p2p;
     // host pipeline (lazily created by sd_compute_host)
     bool host_ready;
     int host_dtype;
@@ -146,15 +157,31 @@ int prof_mark(sd_handle *h, cudaStream_t st) {
 
 // The level screen runs in front of the specialised kernel only: not in the debug / reference-compat modes (they need
 // every level of the volume) and not with an explicitly selected generic or warp-specialised variant.
-bool screen_active(const sd_handle *h) {
+bool screen_allowed(const sd_handle *h) {
     return h->screen && h->s.pass_mask && h->s.padl && (h->variant == 0 || h->variant == 2) && !h->dbg_cost &&
            !h->dbg_agg && !h->s.agg_vol && mbm_screen_supported(h->g);
 }
 
-// 1 generic, 2 specialised, 3 warp-specialised
-int active_variant(const sd_handle *h) {
+// Does the screen pay for a launch of `frames` frames?  Behind the screen a launch cannot finish before its heaviest
+// tile has (a tile that keeps all its level pairs costs as much as an unscreened one), so with less than about two
+// waves of tiles the unscreened kernel is faster.  Model in units of one full tile: unscreened = waves; screened =
+// screen kernel (0.215 tile-times per tile and SM) + max(1 heavy tile, 25 % of the work spread over all slots).
+// With variant 0 only; an explicit variant 2 always screens (tests, tuning).
+bool screen_pays(const sd_handle *h, int frames) {
+    if (h->variant == 2) return true;
+    const PadGeom pg = make_pad_geom(h->g.Hd, h->g.Wd, h->g.L, h->g.min_ds);
+    const double tiles = (double)pg.tiles_x * pg.tiles_y * frames, sms = h->sms, slots = (double)h->sms * h->per_sm_fast;
+    const double unscreened = (double)(long long)((tiles + slots - 1) / slots);
+    const double screened = tiles * 0.215 / sms + (0.25 * tiles / slots > 1.0 ? 0.25 * tiles / slots : 1.0);
+    return screened < 0.95 * unscreened;
+}
+
+bool screen_active(const sd_handle *h, int frames) { return screen_allowed(h) && screen_pays(h, frames); }
+
+// 1 generic, 2 specialised, 3 warp-specialised -- for a launch of `frames` frames
+int active_variant(const sd_handle *h, int frames) {
     const bool fast = h->s.padl && ((h->variant >= 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g)));
-    const bool ws = (h->variant == 3 || (h->variant == 0 && h->auto_ws && !screen_active(h))) && h->s.padl &&
+    const bool ws = (h->variant == 3 || (h->variant == 0 && h->auto_ws && !screen_active(h, frames))) && h->s.padl &&
                     !h->dbg_cost && !h->dbg_agg && mbm_wta_ws_supported(h->g);
     return ws ? 3 : (fast ? 2 : 1);
 }
@@ -169,8 +196,8 @@ int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int 
     if (k0 <= 1 && 1 <= k1) {
         // (reference-compat mode: the kernels also materialise the aggregated volume into h->s.agg_vol)
         h->s.range_epoch = ++h->epoch;
-        const int v = active_variant(h);
-        bool screen = (v == 2) && screen_active(h);
+        const int v = active_variant(h, frames);
+        bool screen = (v == 2) && screen_active(h, frames);
         if (screen && h->stats_host) {
             const unsigned long long w = *(volatile unsigned long long *)h->stats_host;   // [tag:16][screened:24][flagged:24]
             if (w != h->stats_seen) {
@@ -194,7 +221,7 @@ int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int 
     if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
     if (k0 <= 2 && 2 <= k1) SD_CUDA(h, launch_secondary(h->g, frames, h->s, st));
     if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
-    if (k0 <= 3 && 3 <= k1) SD_CUDA(h, launch_fill(h->g, frames, h->s, h->gl_glob, out, st));
+    if (k0 <= 3 && 3 <= k1) SD_CUDA(h, launch_fill(h->g, frames, h->s, h->gv, out, st));
     if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
     return SD_OK;
 }
@@ -301,6 +328,8 @@ int sd_create(const sd_config *cfg, int device, int frames_per_launch, sd_handle
     const PadGeom pgq = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
     const size_t smem_b = (size_t)(kTileH + 20) * 42 * 16 + (size_t)kBandRows * (kBandLW + pgq.rw) * 4;
     const int per_sm_fast = (2 * (smem_b + 1024) <= 227 * 1024) ? 2 : 1;
+    h->sms = sms;
+    h->per_sm_fast = per_sm_fast;
     const long long tiles_x = (g.Wd + kTileW - 1) / kTileW;
     const long long tiles_fast = tiles_x * ((g.Hd + 31) / 32), tiles_ws = tiles_x * ((g.Hd + 63) / 64);
     const size_t per_frame = (size_t)g.H * g.W * 4 * 2 + (size_t)g.Hd * g.Wd * 60;
@@ -391,6 +420,11 @@ int sd_destroy(sd_handle *h) {
         cudaFree(h->s.agg_vol);
         cudaFree(h->s.padl);
         cudaFree(h->s.padr);
+        if (h->p2p.on) {
+            for (int q = 0; q < h->p2p.world; q++)
+                if (q != h->p2p.rank && h->p2p.peer[q]) cudaIpcCloseMemHandle(h->p2p.peer[q]);
+            cudaFree(h->p2p.base);
+        }
         if (h->stats_host) cudaFreeHost(h->stats_host);
         cudaFree(h->s.pass_mask);
         cudaFree(h->s.tile_order);
@@ -449,7 +483,7 @@ int sd_set_band(sd_handle *h, int pooled_row_offset, int global_height, const fl
         h->g.band_x_off = 0;
         h->g.Hd_glob = h->g.Hd;
         h->g.H_glob = h->g.H;
-        h->gl_glob = nullptr;
+        memset(&h->gv, 0, sizeof(h->gv));
         return SD_OK;
     }
     if (global_height % K != 0 || h->g.H % K != 0) return fail(h, SD_ERR_UNSUPPORTED, "band mode needs heights divisible by downscale_factor");
@@ -457,8 +491,131 @@ int sd_set_band(sd_handle *h, int pooled_row_offset, int global_height, const fl
     h->g.band_x_off = pooled_row_offset;
     h->g.H_glob = global_height;
     h->g.Hd_glob = global_height / K;
-    h->gl_glob = global_left_gray;
+    memset(&h->gv, 0, sizeof(h->gv));
+    h->gv.flat = global_left_gray;
     return SD_OK;
+}
+
+// ---- row bands over peer memory ------------------------------------------------------------------------------------
+namespace {
+constexpr size_t kP2PFlagBytes = 4096;
+enum { kFlagFromPrev = 0, kFlagFromNext = 1, kFlagGray = 8, kCtrScatter = 32, kCtrPublish = 33 };
+inline char *p2p_window(const sd_handle *h, int q, int view) { return h->p2p.peer[q] + (size_t)view * h->p2p.win_bytes; }
+inline float *p2p_gray(const sd_handle *h, int q, int parity) {
+    return (float *)(h->p2p.peer[q] + 2 * h->p2p.win_bytes + (size_t)parity * h->p2p.gray_bytes);
+}
+inline unsigned *p2p_flags(const sd_handle *h, int q) { return (unsigned *)(h->p2p.peer[q] + 2 * h->p2p.win_bytes + 2 * h->p2p.gray_bytes); }
+}  // namespace
+
+int sd_band_p2p_init(sd_handle *h, int world, int rank, const int32_t *band_row0, int halo_rows, int dtype, void *ipc_handle_out) {
+    if (!h || !band_row0 || !ipc_handle_out) return SD_ERR_BAD_ARG;
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(h, SD_ERR_BAD_ARG, "peer-memory band mode supports 1..8 ranks");
+    if (dtype != SD_U8 && dtype != SD_F32) return fail(h, SD_ERR_SHAPE, "dtype must be SD_U8 or SD_F32");
+    if (h->p2p.on) return fail(h, SD_ERR_BAD_ARG, "sd_band_p2p_init was already called on this handle");
+    const Geom &g = h->g;
+    const int esize = dtype == SD_U8 ? 1 : 4, K = g.K;
+    if ((g.W * esize) % 16 != 0 || g.W % 4 != 0) return fail(h, SD_ERR_UNSUPPORTED, "peer-memory band mode needs 16-byte image rows");
+    int tallest = 0;
+    for (int q = 0; q < world; q++) {
+        const int rows = band_row0[q + 1] - band_row0[q];
+        if (rows < halo_rows || rows % K != 0 || band_row0[q] % K != 0) return fail(h, SD_ERR_SHAPE, "bands must be multiples of downscale_factor and at least as tall as the halo");
+        if (rows > tallest) tallest = rows;
+    }
+    if (halo_rows % K != 0 || band_row0[0] != 0) return fail(h, SD_ERR_SHAPE, "halo must be a multiple of downscale_factor; bands start at row 0");
+    if (g.H != band_row0[rank + 1] - band_row0[rank] + 2 * halo_rows) return fail(h, SD_ERR_SHAPE, "the handle's height must be band rows + 2 * halo rows");
+    DeviceGuard dg(h->device);
+    if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
+    sd_handle::P2P &p = h->p2p;
+    memset(&p, 0, sizeof(p));
+    p.world = world;
+    p.rank = rank;
+    p.dtype = dtype;
+    p.halo_rows = halo_rows;
+    for (int q = 0; q <= world; q++) p.row0[q] = band_row0[q];
+    p.win_bytes = (((size_t)3 * (tallest + 2 * halo_rows) * g.W * esize) + 255) & ~(size_t)255;
+    p.gray_bytes = (((size_t)tallest * g.W * sizeof(float)) + 255) & ~(size_t)255;
+    const size_t total = 2 * p.win_bytes + 2 * p.gray_bytes + kP2PFlagBytes;
+    SD_CUDA(h, cudaMalloc((void **)&p.base, total));
+    SD_CUDA(h, cudaMemset(p.base, 0, total));
+    SD_CUDA(h, cudaDeviceSynchronize());
+    p.peer[rank] = p.base;
+    cudaIpcMemHandle_t ipc;
+    SD_CUDA(h, cudaIpcGetMemHandle(&ipc, p.base));
+    static_assert(sizeof(ipc) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(ipc_handle_out, &ipc, sizeof(ipc));
+    p.on = true;
+    p.connected = (world == 1);
+    return SD_OK;
+}
+
+int sd_band_p2p_connect(sd_handle *h, const void *ipc_handles) {
+    if (!h || !ipc_handles) return SD_ERR_BAD_ARG;
+    if (!h->p2p.on) return fail(h, SD_ERR_BAD_ARG, "call sd_band_p2p_init first");
+    DeviceGuard dg(h->device);
+    if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
+    sd_handle::P2P &p = h->p2p;
+    for (int q = 0; q < p.world; q++) {
+        if (q == p.rank || p.peer[q]) continue;
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, (const char *)ipc_handles + (size_t)q * sizeof(ipc), sizeof(ipc));
+        SD_CUDA(h, cudaIpcOpenMemHandle((void **)&p.peer[q], ipc, cudaIpcMemLazyEnablePeerAccess));
+    }
+    p.connected = true;
+    return SD_OK;
+}
+
+int sd_band_p2p_compute(sd_handle *h, const void *left_band, const void *right_band, float *out, void *stream) {
+    if (!h) return SD_ERR_BAD_ARG;
+    if (!left_band || !right_band || !out) return fail(h, SD_ERR_BAD_ARG, "null image pointer");
+    sd_handle::P2P &p = h->p2p;
+    if (!p.on || !p.connected) return fail(h, SD_ERR_BAD_ARG, "peer-memory band mode is not connected (sd_band_p2p_init / _connect)");
+    if (h->chunk < 1) return fail(h, SD_ERR_SHAPE, "handle has no scratch");
+    DeviceGuard dg(h->device);
+    if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = order_after_previous(h, st);
+    if (rc != SD_OK) return rc;
+    const Geom &g = h->g;
+    const int W = g.W, esize = p.dtype == SD_U8 ? 1 : 4, r = p.rank, n = p.world;
+    const int prev = (r + n - 1) % n, next = (r + 1) % n;
+    auto rows_of = [&](int q) { return p.row0[q + 1] - p.row0[q]; };
+    const int band_rows = rows_of(r), halo = p.halo_rows;
+    const unsigned epoch = ++p.epoch;
+    unsigned *myflags = p2p_flags(h, r);
+    // exchange step 1, fused with the copy into my own window: halos go straight into the neighbours' HBM
+    SD_CUDA(h, launch_band_scatter(left_band, right_band, p2p_window(h, r, 0), p2p_window(h, r, 1), p2p_window(h, prev, 0),
+                                   p2p_window(h, prev, 1), p2p_window(h, next, 0), p2p_window(h, next, 1), W * esize, band_rows,
+                                   halo, band_rows + 2 * halo, rows_of(prev) + 2 * halo, rows_of(next) + 2 * halo,
+                                   myflags + kCtrScatter, p2p_flags(h, prev) + kFlagFromNext, p2p_flags(h, next) + kFlagFromPrev,
+                                   epoch, st));
+    SD_CUDA(h, launch_wait_flags(myflags, kFlagFromPrev, 2, epoch, st));
+    // gray + pool on the local window [top halo | band | bottom halo]
+    h->g.band_x_off = 0;
+    h->g.Hd_glob = g.Hd;
+    h->g.H_glob = g.H;
+    memset(&h->gv, 0, sizeof(h->gv));
+    rc = run_chunk(h, p2p_window(h, r, 0), p2p_window(h, r, 1), p.dtype, 1, out, st, 0, 0);
+    if (rc != SD_OK) return rc;
+    // exchange step 2: publish my left gray band, tell every rank (myself included)
+    const int parity = (int)(epoch & 1u);
+    unsigned *peer_flags[8];
+    for (int q = 0; q < n; q++) peer_flags[q] = p2p_flags(h, q) + kFlagGray + r;
+    SD_CUDA(h, launch_publish_gray(h->s.gray + (size_t)halo * W, p2p_gray(h, r, parity), (size_t)band_rows * W,
+                                   myflags + kCtrPublish, peer_flags, n, epoch, st));
+    SD_CUDA(h, launch_wait_flags(myflags, kFlagGray, n, epoch, st));
+    // matching + secondary + fill on the window; the fill reads its colour row from whichever rank owns it
+    h->g.band_x_off = (p.row0[r] - halo) / g.K;
+    h->g.H_glob = p.row0[n];
+    h->g.Hd_glob = p.row0[n] / g.K;
+    h->gv.n = n;
+    for (int q = 0; q < n; q++) {
+        h->gv.band[q] = p2p_gray(h, q, parity);
+        h->gv.row0[q] = p.row0[q];
+    }
+    h->gv.row0[n] = p.row0[n];
+    rc = run_chunk(h, nullptr, nullptr, p.dtype, 1, out, st, 1, 3);
+    if (rc != SD_OK) return rc;
+    return mark_last_use(h, st);
 }
 
 int sd_compute_host(sd_handle *h, const void *left, const void *right, int dtype, int n_frames, float *out) {
@@ -573,13 +730,17 @@ int sd_set_variant(sd_handle *h, int variant) {
 int sd_launches_per_call(sd_handle *h, int n_frames) {
     if (!h || n_frames <= 0) return 0;
     // gray+pool, [pad planes for the TMA-staged specialised kernels], [level screen], cost+agg+WTA, secondary, fill
-    const int per_chunk = 4 + (active_variant(h) >= 2 ? 1 : 0) + (active_variant(h) == 2 && screen_active(h) ? 1 : 0);
-    return per_chunk * ((n_frames + h->chunk - 1) / h->chunk);
+    int total = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += h->chunk) {
+        const int nf = (n_frames - f0 < h->chunk) ? n_frames - f0 : h->chunk;
+        total += 4 + (active_variant(h, nf) >= 2 ? 1 : 0) + (active_variant(h, nf) == 2 && screen_active(h, nf) ? 1 : 0);
+    }
+    return total;
 }
 
 int sd_frames_per_launch(sd_handle *h) { return h ? h->chunk : 0; }
 
-int sd_active_variant(sd_handle *h) { return h ? active_variant(h) : 0; }
+int sd_active_variant(sd_handle *h) { return h ? active_variant(h, h->chunk) : 0; }
 
 int sd_set_screen(sd_handle *h, int on) {
     if (!h) return SD_ERR_BAD_ARG;
@@ -592,7 +753,7 @@ int sd_set_screen(sd_handle *h, int on) {
 
 int sd_screen_paused(sd_handle *h) { return h ? h->screen_pause : 0; }
 
-int sd_screen_active(sd_handle *h) { return (h && active_variant(h) == 2 && screen_active(h)) ? 1 : 0; }
+int sd_screen_active(sd_handle *h) { return (h && active_variant(h, h->chunk) == 2 && screen_active(h, h->chunk)) ? 1 : 0; }
 
 int sd_screen_stats(sd_handle *h, double *evaluated_fraction, int reset) {
     if (!h || !evaluated_fraction) return SD_ERR_BAD_ARG;

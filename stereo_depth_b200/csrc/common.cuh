@@ -101,6 +101,16 @@ struct Scratch {
     int range_epoch;                  // (or is NaN): the screen's error bound does not hold, masks are ignored
 };
 
+// Where the GLOBAL left gray image lives in row-band mode (the vertical fill's colour row (K+1)*x can be anywhere in
+// the image, upscale_disparity_vertical_fill.cu:31).  n == 0: one flat [H_glob][W] image `flat` (NULL = the handle's
+// own image, normal mode).  n > 0: rank q holds rows row0[q] .. row0[q+1]-1 at band[q] (peer memory over NVLink).
+struct GrayView {
+    const float *flat;
+    const float *band[8];
+    int row0[9];
+    int n;
+};
+
 // kernel launchers (each returns cudaGetLastError())
 cudaError_t launch_gray_pool(const Geom &g, const void *left, const void *right, int dtype, int frames,
                              const Scratch &s, cudaStream_t st);
@@ -116,6 +126,14 @@ cudaError_t launch_mbm_screen(const Geom &g, int frames, const Scratch &s, cudaS
 bool mbm_wta_ws_supported(const Geom &g);
 cudaError_t launch_mbm_wta_ws(const Geom &g, int frames, const Scratch &s, cudaStream_t st);
 cudaError_t launch_secondary(const Geom &g, int frames, const Scratch &s, cudaStream_t st);
-cudaError_t launch_fill(const Geom &g, int frames, const Scratch &s, const float *gl_glob, float *out, cudaStream_t st);
+cudaError_t launch_fill(const Geom &g, int frames, const Scratch &s, const GrayView &gv, float *out, cudaStream_t st);
+// peer-memory row-band exchange (band_p2p.cu)
+cudaError_t launch_band_scatter(const void *left, const void *right, void *own_l, void *own_r, void *prev_l, void *prev_r,
+                                void *next_l, void *next_r, int row_bytes, int band_rows, int halo, int own_rows, int prev_rows,
+                                int next_rows, unsigned *counter, unsigned *flag_at_prev, unsigned *flag_at_next, unsigned epoch,
+                                cudaStream_t st);
+cudaError_t launch_publish_gray(const float *src, float *dst, size_t n_floats, unsigned *counter, unsigned *const *peer_flags,
+                                int n_peers, unsigned epoch, cudaStream_t st);
+cudaError_t launch_wait_flags(const unsigned *flags, int first, int count, unsigned epoch, cudaStream_t st);
 
 }  // namespace sd

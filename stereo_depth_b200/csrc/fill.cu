@@ -29,9 +29,17 @@ __device__ __forceinline__ float div_k(float x, float fk) {
     return __fdiv_rn(x, fk);
 }
 
-// gl = left gray of this handle's (local) image; glg = left gray of the GLOBAL image (== gl outside band mode).
+// Row `row` of the GLOBAL left gray image (only the rare colour-pick branch gets here).
+__device__ __forceinline__ const float *global_gray_row(const GrayView &gv, const float *gl, int row, int W) {
+    if (gv.n == 0) return (gv.flat ? gv.flat : gl) + (size_t)row * W;
+    int q = 0;
+    while (q + 1 < gv.n && row >= gv.row0[q + 1]) q++;
+    return gv.band[q] + (size_t)(row - gv.row0[q]) * W;
+}
+
+// gl = left gray of this handle's (local) image; glg = where the GLOBAL image lives (== gl outside band mode).
 template <int KT>
-__device__ __forceinline__ float vfill_value(const Geom &g, const float *__restrict__ gl, const float *__restrict__ glg,
+__device__ __forceinline__ float vfill_value(const Geom &g, const float *__restrict__ gl, const GrayView &glg,
                                              const float *__restrict__ disp, int r, int c) {
     const int K = KT > 0 ? KT : g.K, x = r / K, i = r - x * K, yd = c / K;
     const float fk = (float)K;
@@ -42,7 +50,7 @@ __device__ __forceinline__ float vfill_value(const Geom &g, const float *__restr
     if (fabsf(__fsub_rn(p, n)) <= g.threshold)
         return __fadd_rn(p, div_k<KT>(__fmul_rn((float)i, __fsub_rn(n, p)), fk));
     const float prev_color = __ldg(gl + (size_t)(K * x) * g.W + c);
-    const float next_color = __ldg(glg + (size_t)wrapm((K + 1) * xg, g.H_glob) * g.W + c);
+    const float next_color = __ldg(global_gray_row(glg, gl, wrapm((K + 1) * xg, g.H_glob), g.W) + c);
     const float cur = __ldg(gl + (size_t)r * g.W + c);
     return (fabsf(__fsub_rn(cur, prev_color)) <= fabsf(__fsub_rn(cur, next_color))) ? p : n;
 }
@@ -63,7 +71,7 @@ __device__ __forceinline__ float hfill_value(const Geom &g, const float *__restr
 
 // value of the "next" mod-K sample to the right of nk on row r
 template <int KT>
-__device__ __forceinline__ float next_sample(const Geom &g, const float *__restrict__ gl, const float *__restrict__ glg,
+__device__ __forceinline__ float next_sample(const Geom &g, const float *__restrict__ gl, const GrayView &glg,
                                              const float *__restrict__ disp, int r, int nk, float p) {
     const int K = KT > 0 ? KT : g.K;
     if (nk + K < g.W) return vfill_value<KT>(g, gl, glg, disp, r, nk + K);
@@ -74,7 +82,7 @@ __device__ __forceinline__ float next_sample(const Geom &g, const float *__restr
 }
 
 template <int KT>
-__global__ void __launch_bounds__(256) fill_kernel(Geom g, const float *__restrict__ gray, const float *__restrict__ gl_glob,
+__global__ void __launch_bounds__(256) fill_kernel(Geom g, const float *__restrict__ gray, const GrayView glg,
                                                    const float *__restrict__ refined, float *__restrict__ out, bool vec_ok) {
     const int c4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int r = blockIdx.y * blockDim.y + threadIdx.y;
@@ -82,7 +90,6 @@ __global__ void __launch_bounds__(256) fill_kernel(Geom g, const float *__restri
     if (r >= g.H || c4 >= g.W) return;
     const size_t plane = (size_t)g.H * g.W;
     const float *gl = gray + (size_t)frame * 2 * plane;
-    const float *glg = gl_glob ? gl_glob : gl;
     const float *disp = refined + (size_t)frame * g.Hd * g.Wd;
     float *o = out + (size_t)frame * plane + (size_t)r * g.W + c4;
     float v[4];
@@ -110,7 +117,7 @@ __global__ void __launch_bounds__(256) fill_kernel(Geom g, const float *__restri
 
 // K = 2 fast path: a thread produces a 2-row x 4-column output block (rows 2x, 2x+1) from 3 + 3 refined
 // disparities; the rare colour-pick branches fall back to the generic helpers above, so semantics are identical.
-__global__ void __launch_bounds__(256) fill_k2_kernel(Geom g, const float *__restrict__ gray, const float *__restrict__ gl_glob,
+__global__ void __launch_bounds__(256) fill_k2_kernel(Geom g, const float *__restrict__ gray, const GrayView glg,
                                                       const float *__restrict__ refined, float *__restrict__ out) {
     const int c4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int x = blockIdx.y * blockDim.y + threadIdx.y;
@@ -118,7 +125,6 @@ __global__ void __launch_bounds__(256) fill_k2_kernel(Geom g, const float *__res
     if (x >= g.Hd || c4 >= g.W) return;
     const size_t plane = (size_t)g.H * g.W;
     const float *gl = gray + (size_t)frame * 2 * plane;
-    const float *glg = gl_glob ? gl_glob : gl;
     const float *disp = refined + (size_t)frame * g.Hd * g.Wd;
     const int y0 = c4 >> 1;
     const bool has3 = c4 + 4 < g.W;
@@ -157,7 +163,7 @@ __global__ void __launch_bounds__(256) fill_k2_kernel(Geom g, const float *__res
 
 }  // namespace
 
-cudaError_t launch_fill(const Geom &g, int frames, const Scratch &s, const float *gl_glob, float *out, cudaStream_t st) {
+cudaError_t launch_fill(const Geom &g, int frames, const Scratch &s, const GrayView &gl_glob, float *out, cudaStream_t st) {
     dim3 block(32, 8), grid(((g.W + 3) / 4 + 31) / 32, (g.H + 7) / 8, frames);
     const bool vec_ok = (g.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
     if (g.K == 2 && vec_ok) {

@@ -163,6 +163,7 @@ def test_adaptive_screen_pauses_on_flat_scenes():
     cfgobj = cuda_depth.StereoMatchingConfiguration(height=H, width=W, min_disparity=0, max_disparity=127)
     flat = torch.full((n, 3, H, W), 90, dtype=torch.uint8, device="cuda")
     sm = cuda_depth.StereoMatching(cfgobj, frames_per_launch=1)
+    sm.set_variant("fast")   # (variant auto would skip the screen for launches this small)
     assert sm.screen_active and sm.screen_paused == 0
     out = sm.compute_disparity_batch(flat, flat).clone()
     torch.cuda.synchronize()
@@ -172,6 +173,7 @@ def test_adaptive_screen_pauses_on_flat_scenes():
     ls, rs = zip(*[make_pair(H, W, 128, seed=21, frame=f)[:2] for f in range(n)])
     L, R = torch.from_numpy(np.stack(ls)).cuda(), torch.from_numpy(np.stack(rs)).cuda()
     sm2 = cuda_depth.StereoMatching(cfgobj, frames_per_launch=1)
+    sm2.set_variant("fast")
     a = sm2.compute_disparity_batch(L, R).clone()
     torch.cuda.synchronize()
     sm2.compute_disparity_batch(L, R)
@@ -318,6 +320,9 @@ def test_batches_chunks_and_host_path_agree():
                                                     max_disparity=D - 1)
     be = backend.CudaStereoMatchingBackend(cfgobj, frames_per_launch=3)   # 7 frames = 3 chunks (3+3+1)
     assert be.native.frames_per_launch == 3
+    # launches this small are below the screen's break-even (variant auto skips it); pin the screened kernel
+    assert not be.native.screen_active
+    be.native.set_variant("fast")
     singles = np.stack([be.process(torch.from_numpy(L[i]), torch.from_numpy(R[i])).cpu().numpy() for i in range(n)])
     batch = be.process_batch(torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()).cpu().numpy()
     host = be.process_batch(torch.from_numpy(L).pin_memory(), torch.from_numpy(R).pin_memory())

@@ -24,8 +24,9 @@ def _plain(left, right, kw):
     return sm.compute_disparity_map(torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda()).cpu().numpy().copy()
 
 
+@pytest.mark.parametrize("p2p", [False, True])
 @pytest.mark.parametrize("K", [1, 2])
-def test_banded_world1_equals_plain(K):
+def test_banded_world1_equals_plain(K, p2p):
     """World size 1: the band is the whole image and both halos wrap onto it -- must equal the normal path on
     EVERY cell (SAFE padding is truly circular), which checks sd_set_band / sd_compute_range and the fill rules."""
     import torch
@@ -36,9 +37,10 @@ def test_banded_world1_equals_plain(K):
     left, right, _ = make_pair(H, W, D, seed=31)
     kw = dict(height=H, width=W, downscale_factor=K, min_disparity=0, max_disparity=D - 1)
     want = _plain(left, right, kw)
-    sm = BandedStereoMatching(cuda_depth.StereoMatchingConfiguration(**kw))
-    got = sm.compute(torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda()).cpu().numpy()
-    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    sm = BandedStereoMatching(cuda_depth.StereoMatchingConfiguration(**kw), p2p=p2p)
+    for _ in range(3):   # several frames: the flags are epochs, the published gray buffer alternates
+        got = sm.compute(torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda()).cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
 def _band_worker(rank, world, port, H, W, K, D, outdir):
@@ -61,6 +63,19 @@ def _band_worker(rank, world, port, H, W, K, D, outdir):
         full = sm.gather(band)
         torch.cuda.synchronize()
         np.save(os.path.join(outdir, f"band{rank}.npy"), full.cpu().numpy())
+        # the same bands over peer memory (P2P stores + flags instead of NCCL), several frames back to back, the last
+        # one with different content so stale halos / gray rows would show
+        sp = BandedStereoMatching(cuda_depth.StereoMatchingConfiguration(**kw), p2p=True)
+        left2, right2, _ = make_pair(H, W, D, seed=34)
+        for _ in range(3):
+            sp.compute(lb, rb)
+        lb2 = torch.from_numpy(left2[:, p.x0 * K:p.x1 * K].copy()).cuda()
+        rb2 = torch.from_numpy(right2[:, p.x0 * K:p.x1 * K].copy()).cuda()
+        full2 = sp.gather(sp.compute(lb2, rb2))
+        full1 = sp.gather(sp.compute(lb, rb))
+        torch.cuda.synchronize()
+        np.save(os.path.join(outdir, f"p2p{rank}.npy"), full1.cpu().numpy())
+        np.save(os.path.join(outdir, f"p2p_b{rank}.npy"), full2.cpu().numpy())
         # frame sharding: this rank's contiguous chunk of an 6-frame batch
         n = 6
         L, R = make_batch(n, 96, 160, 32, seed=5)
@@ -84,9 +99,13 @@ def test_row_bands_and_frame_shards_over_nccl(tmp_path):
     mp.spawn(_band_worker, args=(world, _free_port(), H, W, K, D, str(tmp_path)), nprocs=world, join=True)
     left, right, _ = make_pair(H, W, D, seed=33)
     want = _plain(left, right, dict(height=H, width=W, downscale_factor=K, min_disparity=0, max_disparity=D - 1))
+    left2, right2, _ = make_pair(H, W, D, seed=34)
+    want2 = _plain(left2, right2, dict(height=H, width=W, downscale_factor=K, min_disparity=0, max_disparity=D - 1))
     for r in range(world):
         got = np.load(tmp_path / f"band{r}.npy")
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"rank {r}"
+        assert np.array_equal(np.load(tmp_path / f"p2p{r}.npy").view(np.uint32), want.view(np.uint32)), f"p2p rank {r}"
+        assert np.array_equal(np.load(tmp_path / f"p2p_b{r}.npy").view(np.uint32), want2.view(np.uint32)), f"p2p (2nd scene) rank {r}"
     L, R = make_batch(6, 96, 160, 32, seed=5)
     import torch
     from stereo_depth_b200 import cuda_depth

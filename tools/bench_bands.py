@@ -30,7 +30,8 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 left, right, _ = make_pair(H, W, D, seed=1234)
 kw = dict(height=H, width=W, downscale_factor=K, min_disparity=0, max_disparity=D - 1)
-sm = BandedStereoMatching(cuda_depth.StereoMatchingConfiguration(**kw))
+P2P = os.environ.get("SD_BANDS_P2P", "1") == "1"
+sm = BandedStereoMatching(cuda_depth.StereoMatchingConfiguration(**kw), p2p=P2P, variant=os.environ.get("SD_BANDS_VARIANT"))
 p = sm.plan
 lb = torch.from_numpy(left[:, p.x0 * K:p.x1 * K].copy()).cuda()
 rb = torch.from_numpy(right[:, p.x0 * K:p.x1 * K].copy()).cuda()
@@ -65,7 +66,8 @@ if rank == 0:
     print(json.dumps({"metric": "frames/s (single 3840x2160 frame, D=256, K=2, row bands)", "n_gpus": world,
                       "ms_per_frame": round(float(ms.item()), 4), "value": round(1000.0 / float(ms.item()), 2),
                       "single_gpu_ms_per_frame": round(s0.elapsed_time(s1) / 5, 4),
-                      "band_rows": p.band_rows, "halo_rows": p.halo_rows, "bit_identical_to_single_gpu": ok,
-                      "exchange": "ring send/recv of 2x24 raw rows per view + all-gather of left gray bands (NCCL)"}), flush=True)
+                      "fused_kernel": sm.handle.active_variant + ("+screen" if sm.handle.screen_active else ""), "band_rows": p.band_rows, "halo_rows": p.halo_rows, "bit_identical_to_single_gpu": ok,
+                      "exchange": ("peer-memory stores of 2x24 raw rows per view + left gray bands read in place over NVLink (flags, no NCCL)"
+                                   if P2P else "ring send/recv of 2x24 raw rows per view + all-gather of left gray bands (NCCL)")}), flush=True)
 if world > 1:
     dist.destroy_process_group()
