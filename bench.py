@@ -282,12 +282,14 @@ def run_ours(args):
         x_ach = 237.0 * Hd * Wd * L * (2.0 * F / x_n) / (x_ms / x_n * 1e-3) / 1e12
         exact_all = {"achieved": round(x_ach, 3), "frac": round(x_ach / FADD_PEAK_TOPS, 4), "launch_ms": round(x_ms / x_n, 4),
                      "how": "mbm_wta_fast_kernel alone with the screen switched off (every level evaluated), profiled after the timed region"}
-    traffic = None
+    traffic, screen_ncu = None, None
     tpath = os.path.join(ROOT, "profiles", "kernelB_traffic.json")
     if os.path.exists(tpath):
         try:
-            per_frame = json.load(open(tpath)).get(args.workload + ("_screened" if screened else "") + "_per_frame")
+            tj = json.load(open(tpath))
+            per_frame = tj.get(args.workload + ("_screened" if screened else "") + "_per_frame")
             traffic = None if per_frame is None else int(per_frame * 2.0 * F / b_n)
+            screen_ncu = tj.get("screen_kernel_ncu") if args.workload == "C3" else None
         except (OSError, ValueError):
             traffic = None
 
@@ -327,7 +329,11 @@ def run_ours(args):
             "note": "achieved/frac count the ALGORITHMIC 237 lane-ops per cell (SURVEY 8-d) over the time of padding + screen + "
                     "exact kernel; the screen proves most level pairs cannot hold the arg-max, so fewer are executed and frac may "
                     "exceed the hardware fraction (and 1).  Results are bit-identical with the screen off.",
-            "exact_kernel_all_levels": exact_all}
+            "exact_kernel_all_levels": exact_all,
+            # the screen kernel itself is bound by the shared-memory crossbar, not by the adders: its ncu figures
+            # (one --set full capture, profiles/r01_ncu_screen_summary.txt), not measured live
+            "screen_kernel": None if screen_ncu is None else dict(screen_ncu, bound="shared-memory crossbar (128 B/clk/SM)",
+                                                                 launch_ms=kernel_ms.get("level_screen"))}
     if world == 1 and not args.no_extras:
         try:
             line["cpu_baseline"] = cpu_baseline_leg(wl)

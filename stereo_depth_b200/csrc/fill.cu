@@ -32,9 +32,16 @@ __device__ __forceinline__ float div_k(float x, float fk) {
 // Row `row` of the GLOBAL left gray image (only the rare colour-pick branch gets here).
 __device__ __forceinline__ const float *global_gray_row(const GrayView &gv, const float *gl, int row, int W) {
     if (gv.n == 0) return (gv.flat ? gv.flat : gl) + (size_t)row * W;
-    int q = 0;
-    while (q + 1 < gv.n && row >= gv.row0[q + 1]) q++;
-    return gv.band[q] + (size_t)(row - gv.row0[q]) * W;
+    // compile-time indices only: the view stays in the kernel's parameter space (no local copy)
+    const float *p = gv.band[0];
+    int first = gv.row0[0];
+#pragma unroll
+    for (int q = 1; q < 8; q++)
+        if (q < gv.n && row >= gv.row0[q]) {
+            p = gv.band[q];
+            first = gv.row0[q];
+        }
+    return p + (size_t)(row - first) * W;
 }
 
 // gl = left gray of this handle's (local) image; glg = where the GLOBAL image lives (== gl outside band mode).

@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "screen or adaptive or batches or ordered" 2>&1 | tail -n 3
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_multi_gpu.py -x -q 2>&1 | tail -n 3
 python bench.py --steps 5 --warmup 3 --no-extras > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench rc=$?"; cat gpurun_out/bench_quick.json

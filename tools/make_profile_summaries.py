@@ -62,12 +62,18 @@ def val(name):
 
 t = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
 ts = 0.0
+screen_ncu = {}
 for rep in ("prof_screen.ncu-rep", "prof_kernelB_screened.ncu-rep"):
     raw = subprocess.run(["ncu", "-i", os.path.join(G, rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, d = rows[0], rows[1], rows[2]
     ts += val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
-json.dump({"C3_per_frame": t / 8, "C3_screened_per_frame": ts / 8,
+    if rep == "prof_screen.ncu-rep":
+        for key, name in (("shared_wavefronts_pct_of_peak", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+                          ("issue_active_pct", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                          ("fma_pipe_active_pct", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active")):
+            screen_ncu[key] = float(d[hdr.index(name)])
+json.dump({"C3_per_frame": t / 8, "C3_screened_per_frame": ts / 8, "screen_kernel_ncu": screen_ncu,
            "note": "(dram__bytes_read.sum + dram__bytes_write.sum) / 8 of one launch over 8 frames of C3 (ncu --set full): C3_per_frame = "
                    "mbm_wta_fast_kernel evaluating all levels (profiles/r01_ncu_kernelB_summary.txt); C3_screened_per_frame = mbm_screen_kernel + "
                    "mbm_wta_fast_kernel behind the screen (r01_ncu_screen_summary.txt, r01_ncu_kernelB_screened_summary.txt); bench.py scales it by "
