@@ -256,6 +256,23 @@ def test_full_size_c2_vs_oracle(variant):
         assert mismatch(got[st], ref[st]) == 0, st
 
 
+@pytest.mark.parametrize("name,H,W,K,D", [("C5", 720, 1280, 2, 128), ("C4", 2160, 3840, 2, 256)])
+def test_full_size_c4_c5_vs_oracle(name, H, W, K, D):
+    """BASELINE configs C4 (3840x2160, D=256: L=128, the largest screened configuration) and C5 (1280x720, D=128):
+    one frame, default schedule (level screen on), WTA / refined / filled bit-exact vs the oracle."""
+    kw = cfg_kw(H, W, K, 0, D - 1)
+    l, r, _ = make_pair(H, W, D, seed=4321)
+    ref = O.run(O.make_config(**kw), l, r, want=("wta", "refined", "out"))
+    info = {}
+    got = run_cuda_all_stages(l, r, kw, variant="fast", volumes=False, info=info)
+    assert info["screen_active"] and info["evaluated_fraction"] < 0.6, info
+    for st in ("wta", "refined", "out"):
+        assert mismatch(got[st], ref[st]) == 0, (name, st)
+    got = run_cuda_all_stages(l, r, kw, variant="auto", volumes=False, frames_per_launch=1)
+    for st in ("wta", "refined", "out"):
+        assert mismatch(got[st], ref[st]) == 0, (name, st, "auto")
+
+
 def test_generic_equals_fast_at_full_size():
     H, W, K, D = 720, 1280, 2, 128
     kw = cfg_kw(H, W, K, 0, D - 1)
