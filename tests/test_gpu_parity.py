@@ -131,7 +131,7 @@ def test_screen_on_equals_screen_off_hard_scenes(kind, K, D):
     for st in ("wta", "refined", "out"):
         assert mismatch(on[st], ref[st]) == 0, (st, kind, info)
     if kind in ("flat", "dark"):
-        assert info["evaluated_fraction"] > (0.9 if kind == "dark" else 0.5), info
+        assert info["evaluated_fraction"] > (0.9 if kind == "dark" else 0.3), info
 
 
 @pytest.mark.parametrize("name", golden_cases())
