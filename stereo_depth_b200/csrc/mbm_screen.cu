@@ -3,30 +3,39 @@
 // The fused kernel must evaluate every window sum as the reference's sequential fp32 chain (204 adds per
 // (pixel, level) cell) because the arg-max is sensitive to the summation order.  But only the levels that can
 // still BE the arg-max need that treatment.  This kernel computes every aggregated cost approximately -- the same
-// fp32 taps, summed separably (3x3 cost -> nested vertical 3/9/21-row sums -> sliding horizontal 21/9/3-column
-// sums; ~45 lane-ops per cell instead of 237) -- and keeps, per pixel, the set of level pairs whose approximate
-// cost is within a RIGOROUS error bound of the pixel's approximate maximum.  The union over a 32x64 tile of those
-// levels and their two neighbours (the secondary matching reads A[d*-1], A[d*+1]; circular,
-// secondary_matching.cu:28-31), as level pairs, is the tile's pass mask: mbm_wta_fast_kernel then runs its exact passes only for those level pairs.  Results are
-// bit-identical to evaluating all levels (tests/test_gpu_parity.py runs both ways):
+// fp32 differences l-r as the reference, |l-r| summed separably (3-tap row sum -> 3x3 -> nested vertical 3/9/21-row
+// sums -> sliding horizontal 21/9/3-column sums; ~45 lane-ops per cell instead of 237) -- and keeps, per pixel, the set
+// of levels whose approximate cost is within a RIGOROUS error bound of the pixel's approximate maximum.  The union over
+// a 32x64 tile of those levels and their two neighbours (the secondary matching reads A[d*-1], A[d*+1]; circular,
+// secondary_matching.cu:28-31), as level pairs, is the tile's pass mask: mbm_wta_fast_kernel then runs its exact
+// passes only for those pairs.  Results are bit-identical to evaluating all levels (tests/test_gpu_parity.py runs both
+// ways).  The bound:
 //
-//   * taps  t = 255 - |l - r|  are computed exactly like the reference (device_functions.cuh:66-70), so both sides
-//     sum the SAME fp32 numbers; for pooled values in [0, 255] every tap is >= 0 and every window sum S satisfies
-//     |S_ref - S| <= 89 u S_max and |S_screen - S| <= 60 u S_max  (u = 2^-24, S_max = 63*9*255 resp. 81*9*255):
-//     below 1.5 in absolute terms; the analysis below uses E = 4.
-//   * a pixel whose approximate maximum A'max is >= T = 2^15 * 144600 * 185910 has all three sums of that level
+//   * The reference's tap is t = fl(255 - |a|), a = fl(l - r) (device_functions.cuh:66-70).  The screen forms the same
+//     a and sums |a| (dissimilarities); N*255 - sum|a| differs from the real sum of the reference's taps by at most
+//     N*255*u (u = 2^-24).  For pooled values in [0, 255] all terms are >= 0, so every fp32 summation order has a
+//     relative error below (#additions on the longest path) * u: the reference's chains stay within 89 u S_max of the
+//     real sum, the screen (12 nested adds, at most 35 sliding-window operations, one final subtraction) within
+//     50 u S_max, with S_max = 63*9*255 resp. 81*9*255: together below 1.5 in absolute terms; the analysis uses E = 4.
+//   * A pixel whose approximate maximum A'max is >= T = 2^15 * 144600 * 185910 has all three sums of that level
 //     >= F = 2^15, hence A_ref[max] >= A'max (1 - 3.7e-4).  A level with A' < (1 - 2e-3) A'max has
 //     A_ref <= (H'+E)(V'+E)(C'+E)(1+2u) < A'max (1 - 3.7e-4)  (all sums >= F/2: factor (1 + E/(F/2))^3 = 1.00073;
 //     else the product is < 4.41e14 < T/2) -- it cannot be the reference's arg-max and is dropped.
-//   * pixels with A'max < T (never seen on image data: mean tap < 58 of 255) flag every pass of their tile;
+//   * The per-pixel set is maintained on the fly: a level enters when A' >= kKeep * running max; the set is cleared
+//     when a new value exceeds kClear * running max (then everything seen so far is below (1-eps) of the final
+//     maximum, kClear - 1 >= eps / (1 - eps)).  It is therefore always a superset of {A' >= kKeep * final max}.
+//   * Pixels with A'max < T (mean tap < 58 of 255: not seen on image data) flag every pair of their tile;
 //     out-of-range float inputs (pooled value outside [0, 255] or NaN) are detected by pad_pooled_kernel and
 //     make the fused kernel ignore the masks altogether.
 //
-// Layout: one block per 32x64 tile (the fused kernel's tile), 256 threads = two groups of 128 that share the
-// TMA-staged row bands and screen the even resp. odd level pairs independently (named barriers), each with its
-// own three row-sum buffers.  Phase A: thread = one of the 84 cost columns, walks the 54 band rows with all
-// running sums in registers (all-positive nested sums: Y3 -> Z9 -> W21).  Phase B: thread = (row, 16 columns),
-// sliding sums along the row, product, candidate bookkeeping (running max + bit set with conservative clearing).
+// Layout: one block per 32x64 tile (the fused kernel's tile); 3 groups of 128 threads (2 when three do not fit the
+// shared memory or L > 96) share the TMA-staged row bands and screen disjoint level pairs (pair m belongs to group
+// m mod NG; named barriers per group), each with its own three row-sum buffers.  Phase A: thread = one of the 84 cost
+// columns, walks the 54 band rows as a software pipeline with all running sums in registers (all-positive nested sums:
+// Y3 -> Z9 -> W21).  Phase B: thread = (row, 16 columns): sliding sums along the row, similarities, product, candidate
+// bookkeeping.  At the end the groups exchange their per-pixel maxima, drop the sets that another group's maximum
+// overrules, and thread 0 writes the tile's mask, its cost class (heaviest-first schedule of the fused kernel) and the
+// statistics that feed the adaptive policy in api.cu.
 #include "common.cuh"
 #include "mbm_helpers.cuh"
 
