@@ -76,6 +76,18 @@ def _band_worker(rank, world, port, H, W, K, D, outdir):
         torch.cuda.synchronize()
         np.save(os.path.join(outdir, f"p2p{rank}.npy"), full1.cpu().numpy())
         np.save(os.path.join(outdir, f"p2p_b{rank}.npy"), full2.cpu().numpy())
+        # uneven bands (pooled rows not divisible by the world size), float32 input, both transports
+        Hu = H + 2 * K
+        leftu, rightu, _ = make_pair(Hu, W, D, seed=35)
+        kwu = dict(kw, height=Hu)
+        for name, p2p in (("nccl", False), ("p2p", True)):
+            su = BandedStereoMatching(cuda_depth.StereoMatchingConfiguration(**kwu), p2p=p2p)
+            pu = su.plan
+            lbu = torch.from_numpy(leftu[:, pu.x0 * K:pu.x1 * K].copy()).float().cuda()
+            rbu = torch.from_numpy(rightu[:, pu.x0 * K:pu.x1 * K].copy()).float().cuda()
+            fullu = su.gather(su.compute(lbu, rbu))
+            torch.cuda.synchronize()
+            np.save(os.path.join(outdir, f"uneven_{name}{rank}.npy"), fullu.cpu().numpy())
         # frame sharding: this rank's contiguous chunk of an 6-frame batch
         n = 6
         L, R = make_batch(n, 96, 160, 32, seed=5)
@@ -106,6 +118,13 @@ def test_row_bands_and_frame_shards_over_nccl(tmp_path):
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"rank {r}"
         assert np.array_equal(np.load(tmp_path / f"p2p{r}.npy").view(np.uint32), want.view(np.uint32)), f"p2p rank {r}"
         assert np.array_equal(np.load(tmp_path / f"p2p_b{r}.npy").view(np.uint32), want2.view(np.uint32)), f"p2p (2nd scene) rank {r}"
+    Hu = H + 2 * K
+    leftu, rightu, _ = make_pair(Hu, W, D, seed=35)
+    wantu = _plain(leftu, rightu, dict(height=Hu, width=W, downscale_factor=K, min_disparity=0, max_disparity=D - 1))
+    for r in range(world):
+        for name in ("nccl", "p2p"):
+            got = np.load(tmp_path / f"uneven_{name}{r}.npy")
+            assert np.array_equal(got.view(np.uint32), wantu.view(np.uint32)), f"uneven {name} rank {r}"
     L, R = make_batch(6, 96, 160, 32, seed=5)
     import torch
     from stereo_depth_b200 import cuda_depth
