@@ -28,9 +28,10 @@
 //     out-of-range float inputs (pooled value outside [0, 255] or NaN) are detected by pad_pooled_kernel and
 //     make the fused kernel ignore the masks altogether.
 //
-// Layout: one block per 32x64 tile (the fused kernel's tile); 3 groups of 128 threads (2 when three do not fit the
-// shared memory or L > 96) share the TMA-staged row bands and screen disjoint level pairs (pair m belongs to group
-// m mod NG; named barriers per group), each with its own three row-sum buffers.  Phase A: thread = one of the 84 cost
+// Layout: one block per 32x64 tile (the fused kernel's tile) of NG groups of 128 threads.  NG = 1 with two blocks per
+// SM for L <= 64; for larger L (the row bands grow with L) one block per SM whose 3 or 2 groups share the TMA-staged
+// row bands and screen disjoint level pairs (pair m belongs to group m mod NG; named barriers per group), each with
+// its own three row-sum buffers.  Phase A: thread = one of the 84 cost
 // columns, walks the 54 band rows as a software pipeline with all running sums in registers (all-positive nested sums:
 // Y3 -> Z9 -> W21).  Phase B: thread = (row, 16 columns): sliding sums along the row, similarities, product, candidate
 // bookkeeping.  At the end the groups exchange their per-pixel maxima, drop the sets that another group's maximum
@@ -168,7 +169,7 @@ __device__ __forceinline__ void screen_phase_a(const float *__restrict__ pl, con
 // MaskT: candidate set of one pixel, two bits per level pair screened by the thread's group (bit 2j = level 2m,
 // bit 2j+1 = level 2m+1 for the group's j-th pair m = j*NG + group): 32 bits hold 16 pairs per group, 64 bits 32.
 template <int NG, typename MaskT>
-__global__ void __launch_bounds__(NG * SGT, 1)
+__global__ void __launch_bounds__(NG * SGT, NG == 1 ? 2 : 1)
 mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const float *__restrict__ padr,
                   unsigned *__restrict__ pass_mask, unsigned long long *__restrict__ stats, int *__restrict__ tile_order,
                   int *__restrict__ bucket_count, unsigned long long *__restrict__ host_word, int epoch) {
@@ -423,6 +424,11 @@ cudaError_t launch_mbm_screen(const Geom &g, int frames, const Scratch &s, cudaS
     if (!mbm_screen_supported(g) || !s.padl || !s.padr || !s.pass_mask || !s.tile_order || !s.bucket_count) return cudaErrorNotSupported;
     // three groups (12 warps) when their buffers fit next to the row bands and 16 pairs per group suffice, else two
     const int M = ((g.L + 1) & ~1) / 2;
+    // Best measured: ONE group per block and two blocks per SM (the group sees every pair of its tile, so its running
+    // maxima settle early and there is no cross-group merge) -- possible while 2 x (bands + buffers) fit the SM's shared
+    // memory and 64 bits hold two bits per pair (L <= 64).  Else one block per SM with 3 or 2 groups sharing the bands.
+    if (M <= 32 && 2 * (screen_smem_bytes(g.L, g.min_ds, 1) + 1024) <= 227 * 1024)
+        return launch_screen_t<1, unsigned long long>(g, frames, s, st);
     if (screen_smem_bytes(g.L, g.min_ds, 3) + 1024 <= 227 * 1024 && M <= 48) return launch_screen_t<3, unsigned>(g, frames, s, st);
     return launch_screen_t<2, unsigned long long>(g, frames, s, st);
 }

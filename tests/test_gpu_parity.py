@@ -130,8 +130,8 @@ def test_screen_on_equals_screen_off_hard_scenes(kind, K, D):
         assert mismatch(on[st], off[st]) == 0, (st, kind, info)
     for st in ("wta", "refined", "out"):
         assert mismatch(on[st], ref[st]) == 0, (st, kind, info)
-    if kind in ("flat", "dark"):
-        assert info["evaluated_fraction"] > (0.9 if kind == "dark" else 0.3), info
+    if kind == "dark":   # similarity sums below the bound's floor: the screen must keep everything
+        assert info["evaluated_fraction"] > 0.9, info
 
 
 @pytest.mark.parametrize("name", golden_cases())
