@@ -451,10 +451,14 @@ int sd_compute(sd_handle *h, const void *left, const void *right, int dtype, int
     int rc = order_after_previous(h, st);
     if (rc != SD_OK) return rc;
     const size_t inb = in_bytes_per_frame(h, dtype), outn = (size_t)h->g.H * h->g.W;
-    for (int f0 = 0; f0 < n_frames; f0 += h->chunk) {
-        const int nf = (n_frames - f0 < h->chunk) ? n_frames - f0 : h->chunk;
+    // Launches of (nearly) equal size rather than full chunks plus a short remainder: behind the level screen a short
+    // launch is dominated by its heaviest tiles.
+    const int nchunks = (n_frames + h->chunk - 1) / h->chunk, base = n_frames / nchunks, extra = n_frames % nchunks;
+    for (int c = 0, f0 = 0; c < nchunks; c++) {
+        const int nf = base + (c < extra ? 1 : 0);
         rc = run_chunk(h, (const char *)left + inb * f0, (const char *)right + inb * f0, dtype, nf, out + outn * f0, st);
         if (rc != SD_OK) return rc;
+        f0 += nf;
     }
     return mark_last_use(h, st);
 }
@@ -731,8 +735,9 @@ int sd_launches_per_call(sd_handle *h, int n_frames) {
     if (!h || n_frames <= 0) return 0;
     // gray+pool, [pad planes for the TMA-staged specialised kernels], [level screen], cost+agg+WTA, secondary, fill
     int total = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += h->chunk) {
-        const int nf = (n_frames - f0 < h->chunk) ? n_frames - f0 : h->chunk;
+    const int nchunks = (n_frames + h->chunk - 1) / h->chunk, base = n_frames / nchunks, extra = n_frames % nchunks;
+    for (int c = 0; c < nchunks; c++) {   // the same split as sd_compute
+        const int nf = base + (c < extra ? 1 : 0);
         total += 4 + (active_variant(h, nf) >= 2 ? 1 : 0) + (active_variant(h, nf) == 2 && screen_active(h, nf) ? 1 : 0);
     }
     return total;

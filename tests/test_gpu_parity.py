@@ -335,7 +335,7 @@ def test_batches_chunks_and_host_path_agree():
     L, R = np.stack(ls), np.stack(rs)
     cfgobj = cuda_depth.StereoMatchingConfiguration(height=H, width=W, downscale_factor=K, min_disparity=0,
                                                     max_disparity=D - 1)
-    be = backend.CudaStereoMatchingBackend(cfgobj, frames_per_launch=3)   # 7 frames = 3 chunks (3+3+1)
+    be = backend.CudaStereoMatchingBackend(cfgobj, frames_per_launch=3)   # 7 frames = 3 chunks (3+2+2)
     assert be.native.frames_per_launch == 3
     # launches this small are below the screen's break-even (variant auto skips it); pin the screened kernel
     assert not be.native.screen_active
