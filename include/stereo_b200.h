@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define SD_ABI_VERSION 1
+#define SD_ABI_VERSION 2   /* 2: level screen, peer-memory row bands, detailed profile read (additions only) */
 
 /* Replaces struct stereo_matching_configuration
  * (src/csrc/depth/stereo_matching_configuration.hh:5-17); field order = the pybind ctor's
