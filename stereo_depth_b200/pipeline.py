@@ -3,8 +3,11 @@ reference's scripts can run against this backend:
 
   DepthEstimationPipelineConfig / Result / Context / DepthEstimationPipeline
       <- src/python/pipeline/depth_estimation_pipeline.py:14-87
-  run_depth_estimation_pipeline
-      <- src/python/pipeline/depth_estimation_pipeline_runner.py:38-66
+  run_depth_estimation_pipeline, run_depth_estimation_pipeline_evaluation, reduce_metrics
+      <- src/python/pipeline/depth_estimation_pipeline_runner.py:28-94
+  D1Metric, ThresholdMetric, MAEMetric
+      <- src/python/pipeline/depth_estimation_pipeline_metrics.py:18-56 (one fused GPU pass instead of three masked
+         tensor expressions: stereo_depth_b200/csrc/consumers.cu)
 
 Right-view synthesis (Deep3D) and the DNN backends are out of scope: `process` needs the right view, or a
 user-supplied `right_view_synthesis` object with a `.process(left)` method.
@@ -14,7 +17,7 @@ from __future__ import annotations
 import time
 from contextlib import contextmanager
 from dataclasses import dataclass
-from typing import Any, Iterable, Optional, Tuple
+from typing import Any, Dict, Iterable, List, Optional, Tuple
 
 import torch
 
@@ -121,3 +124,85 @@ def run_depth_estimation_pipeline(image_pairs: Iterable[Tuple[torch.Tensor, torc
             hook.process(context)
     for hook in hooks:
         hook.on_pipeline_end()
+
+
+class DepthEstimationPipelineMetric:
+    """Interface of depth_estimation_pipeline_metrics.py:7-15.  The built-in metrics are evaluated together by one fused
+    kernel over the runner's mask `0 < gt <= max_disparity` (runner.py:85); `process` keeps the reference's signature
+    for metrics a user brings along."""
+
+    def name(self) -> str:
+        raise NotImplementedError
+
+    def process(self, disparity_estimate: torch.Tensor, disparity_gt: torch.Tensor, mask: torch.Tensor) -> float:
+        raise NotImplementedError
+
+
+class D1Metric(DepthEstimationPipelineMetric):
+    def name(self) -> str:
+        return "D1"
+
+    def process(self, disparity_estimate, disparity_gt, mask):
+        e = torch.abs(disparity_estimate[mask] - disparity_gt[mask])
+        return torch.mean(((e > 3) & (e / disparity_gt[mask].abs() > 0.05)).float()).item()
+
+
+class ThresholdMetric(DepthEstimationPipelineMetric):
+    def __init__(self, threshold: float):
+        self._threshold = threshold
+
+    def name(self) -> str:
+        return f"Threshold_{int(self._threshold)}"
+
+    def process(self, disparity_estimate, disparity_gt, mask):
+        e = torch.abs(disparity_estimate[mask] - disparity_gt[mask])
+        return torch.mean((e > self._threshold).float()).item()
+
+
+class MAEMetric(DepthEstimationPipelineMetric):
+    def name(self) -> str:
+        return "MAE"
+
+    def process(self, disparity_estimate, disparity_gt, mask):
+        return torch.nn.functional.l1_loss(disparity_estimate[mask], disparity_gt[mask]).item()
+
+
+def reduce_metrics(metrics_results: Dict[str, List[float]], reduction: str) -> Dict[str, float]:
+    """runner.py:28-35."""
+    ops = {"mean": lambda x: sum(x) / len(x), "sum": sum}
+    return {key: ops[reduction](value) for key, value in metrics_results.items()}
+
+
+def run_depth_estimation_pipeline_evaluation(frames_with_gt: Iterable[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]],
+                                             pipeline: DepthEstimationPipeline,
+                                             metrics: Iterable[DepthEstimationPipelineMetric] = None,
+                                             reduction: str = "mean", verbose: bool = True) -> Dict[str, float]:
+    """Evaluation loop of runner.py:69-94 over any iterable of (left, right, gt_disparity).  D1 / Threshold_n / MAE come
+    from ONE fused pass per frame (consumers.evaluate, mask 0 < gt <= max_disparity); any other metric object is called
+    with the reference's (estimate, gt, mask) arguments."""
+    from . import consumers
+    metrics = list(metrics or [])
+    results: Dict[str, List[float]] = {m.name(): [] for m in metrics}
+    config = pipeline.get_configuration()
+    max_disp = config.max_disparity
+    for frame_index, (left_view, right_view, gt_disparity) in enumerate(frames_with_gt):
+        if tuple(left_view.shape[-2:]) != tuple(config.image_shape):
+            raise RuntimeError(f"Incompatible image shapes between pipeline configuration and camera."
+                               f"Pipeline expects: {config.image_shape} but camera provides: {tuple(left_view.shape[-2:])}.")
+        gt_disparity = gt_disparity.cuda().float()
+        result = pipeline.process(left_view, right_view)
+        fused: Dict[float, Dict[str, float]] = {}
+        mask = None
+        for m in metrics:
+            thr = m._threshold if isinstance(m, ThresholdMetric) else 3.0
+            if type(m) in (D1Metric, ThresholdMetric, MAEMetric):
+                if thr not in fused:
+                    fused[thr] = consumers.evaluate(result.disparity_map, gt_disparity, max_disp, threshold=thr)
+                results[m.name()].append(fused[thr][m.name()])
+            else:
+                if mask is None:
+                    mask = (gt_disparity <= max_disp) & (gt_disparity > 0)
+                results[m.name()].append(m.process(result.disparity_map, gt_disparity, mask))
+        if verbose:
+            print(f"Processed frame {frame_index}.")
+    return reduce_metrics(results, reduction)
