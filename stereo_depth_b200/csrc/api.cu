@@ -62,7 +62,7 @@ struct sd_handle {
     // optional per-kernel timing (sd_profile_enable): kProfMarks events per chunk on the launching stream
     bool prof;
     std::vector<cudaEvent_t> *prof_events;
-    char err[320];
+    char err[640];
     int last_cuda;
 };
 
@@ -540,11 +540,16 @@ int sd_band_p2p_init(sd_handle *h, int world, int rank, const int32_t *band_row0
     p.gray_bytes = (((size_t)tallest * g.W * sizeof(float)) + 255) & ~(size_t)255;
     const size_t total = 2 * p.win_bytes + 2 * p.gray_bytes + kP2PFlagBytes;
     SD_CUDA(h, cudaMalloc((void **)&p.base, total));
-    SD_CUDA(h, cudaMemset(p.base, 0, total));
-    SD_CUDA(h, cudaDeviceSynchronize());
-    p.peer[rank] = p.base;
     cudaIpcMemHandle_t ipc;
-    SD_CUDA(h, cudaIpcGetMemHandle(&ipc, p.base));
+    cudaError_t e = cudaMemset(p.base, 0, total);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&ipc, p.base);
+    if (e != cudaSuccess) {
+        cudaFree(p.base);
+        p.base = nullptr;
+        return fail_cuda(h, e, "sd_band_p2p_init (memset / cudaIpcGetMemHandle)");
+    }
+    p.peer[rank] = p.base;
     static_assert(sizeof(ipc) == 64, "cudaIpcMemHandle_t is 64 bytes");
     memcpy(ipc_handle_out, &ipc, sizeof(ipc));
     p.on = true;
