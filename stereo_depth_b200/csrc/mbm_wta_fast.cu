@@ -71,16 +71,20 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
     int tile = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     if (tile_order) {
         const int nt = gridDim.x * gridDim.y * gridDim.z;
-        int rem = tile;
+        int cnt[kScreenBuckets];
+#pragma unroll
+        for (int b = 0; b < kScreenBuckets; b++) cnt[b] = __ldg(bucket_count + b);   // independent loads, one round trip
+        int rem = tile, slot = 0;
+        bool found = false;
 #pragma unroll
         for (int b = kScreenBuckets - 1; b >= 0; b--) {
-            const int c = bucket_count[b];
-            if (rem < c) {
-                tile = tile_order[b * nt + rem];
-                break;
+            if (!found && rem < cnt[b]) {
+                slot = b * nt + rem;
+                found = true;
             }
-            rem -= c;
+            if (!found) rem -= cnt[b];
         }
+        if (found) tile = tile_order[slot];
     }
     const int tile_x = tile % gridDim.x, tile_y = (tile / gridDim.x) % gridDim.y;
     const int frame = tile / (gridDim.x * gridDim.y), r0 = tile_y * BH, c0 = tile_x * BW;
