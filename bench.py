@@ -127,8 +127,7 @@ def dist_setup(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        pin_to_gpu_numa_node(local)
+    pin_to_gpu_numa_node(local)   # also with one GPU: the pinned buffers of the e2e leg should be first-touched near it
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
