@@ -28,15 +28,14 @@
 //     out-of-range float inputs (pooled value outside [0, 255] or NaN) are detected by pad_pooled_kernel and
 //     make the fused kernel ignore the masks altogether.
 //
-// Layout: one block per 32x64 tile (the fused kernel's tile) of NG groups of 128 threads.  NG = 1 with two blocks per
-// SM for L <= 64; for larger L (the row bands grow with L) one block per SM whose 3 or 2 groups share the TMA-staged
-// row bands and screen disjoint level pairs (pair m belongs to group m mod NG; named barriers per group), each with
-// its own three row-sum buffers.  Phase A: thread = one of the 84 cost
-// columns, walks the 54 band rows as a software pipeline with all running sums in registers (all-positive nested sums:
-// Y3 -> Z9 -> W21).  Phase B: thread = (row, 16 columns): sliding sums along the row, similarities, product, candidate
-// bookkeeping.  At the end the groups exchange their per-pixel maxima, drop the sets that another group's maximum
-// overrules, and thread 0 writes the tile's mask, its cost class (heaviest-first schedule of the fused kernel) and the
-// statistics that feed the adaptive policy in api.cu.
+// Layout: one block of 128 threads per 32x64 tile (the fused kernel's tile), two blocks per SM (110 KB each: the
+// TMA-staged row bands + three row-sum buffers).  The block sees every level pair of its tile in ascending order, so
+// its running maxima settle early and the candidate bookkeeping goes quiet.  For L > 64 the right band is staged one
+// window of 32 level pairs at a time.  Phase A: thread = one of the 84 cost columns, walks the 54 band rows as a
+// software pipeline with all running sums in registers (all-positive nested sums: Y3 -> Z9 -> W21).  Phase B: thread =
+// (row, 16 columns): sliding sums along the row, similarities, product, candidate bookkeeping.  At the end thread 0
+// writes the tile's mask, its cost class (heaviest-first schedule of the fused kernel) and the statistics that feed the
+// adaptive policy in api.cu.
 #include "common.cuh"
 #include "mbm_helpers.cuh"
 
@@ -62,6 +61,10 @@ constexpr float kHVmax = 63.0f * 9.0f * 255.0f, kCmax = 81.0f * 9.0f * 255.0f;  
 
 __host__ __device__ inline size_t screen_smem_bytes(int L, int min_ds, int groups) {
     return (size_t)groups * SBUF * sizeof(float2) + (size_t)SBR * (LW + make_pad_geom(64, 64, L, min_ds).rw) * 4;
+}
+
+__host__ __device__ inline size_t screen_smem_bytes_windowed() {
+    return (size_t)SBUF * sizeof(float2) + (size_t)SBR * (LW + 152) * 4;
 }
 
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(SGT) : "memory"); }
@@ -166,15 +169,51 @@ __device__ __forceinline__ void screen_phase_a(const float *__restrict__ pl, con
     }
 }
 
-// MaskT: candidate set of one pixel, two bits per level pair screened by the thread's group (bit 2j = level 2m,
-// bit 2j+1 = level 2m+1 for the group's j-th pair m = j*NG + group): 32 bits hold 16 pairs per group, 64 bits 32.
-template <int NG, typename MaskT>
-__global__ void __launch_bounds__(NG * SGT, NG == 1 ? 2 : 1)
+// ---- candidate-set words ----------------------------------------------------------------------------------------------
+struct Mask128 {
+    unsigned long long lo, hi;
+};
+template <typename T> __device__ __forceinline__ T m_zero() { return (T)0; }
+template <> __device__ __forceinline__ Mask128 m_zero<Mask128>() { return Mask128{0ull, 0ull}; }
+template <typename T> __device__ __forceinline__ T m_bit(int idx) { return (T)1 << idx; }
+template <> __device__ __forceinline__ Mask128 m_bit<Mask128>(int idx) {
+    return Mask128{idx < 64 ? 1ull << idx : 0ull, idx >= 64 ? 1ull << (idx - 64) : 0ull};
+}
+template <typename T> __device__ __forceinline__ void m_or(T &a, const T &b) { a |= b; }
+__device__ __forceinline__ void m_or(Mask128 &a, const Mask128 &b) { a.lo |= b.lo; a.hi |= b.hi; }
+template <typename T> __device__ __forceinline__ bool m_any(const T &a) { return a != 0; }
+__device__ __forceinline__ bool m_any(const Mask128 &a) { return (a.lo | a.hi) != 0ull; }
+template <typename T> __device__ __forceinline__ bool m_test(const T &a, int idx) { return ((a >> idx) & 1) != 0; }
+__device__ __forceinline__ bool m_test(const Mask128 &a, int idx) { return (((idx < 64 ? a.lo : a.hi) >> (idx & 63)) & 1ull) != 0ull; }
+__device__ __forceinline__ unsigned warp_or(unsigned v) { return __reduce_or_sync(0xffffffffu, v); }
+__device__ __forceinline__ unsigned long long warp_or(unsigned long long v) {
+    return ((unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)(v >> 32)) << 32) | __reduce_or_sync(0xffffffffu, (unsigned)v);
+}
+__device__ __forceinline__ Mask128 warp_or(const Mask128 &v) { return Mask128{warp_or(v.lo), warp_or(v.hi)}; }
+__device__ __forceinline__ void shared_or(unsigned *p, unsigned v) { atomicOr(p, v); }
+__device__ __forceinline__ void shared_or(unsigned long long *p, unsigned long long v) { atomicOr(p, v); }
+__device__ __forceinline__ void shared_or(Mask128 *p, const Mask128 &v) {
+    if (v.lo) atomicOr(&p->lo, v.lo);
+    if (v.hi) atomicOr(&p->hi, v.hi);
+}
+
+constexpr int SWIN = 152;       // right-band window (floats) of the windowed schedule: 32 level pairs + 84 cost columns + taps
+constexpr int SWPASS = 32;      // level pairs per window
+
+// MaskT: candidate set of one pixel, two bits per level pair (bit 2m = level 2m, bit 2m+1 = level 2m+1): 64 bits for
+// L <= 64, 128 bits up to L = 128.
+// WIN: the right row band is staged one window of SWPASS level pairs at a time (SWIN columns) instead of whole, so the
+// shared-memory footprint does not grow with L and two blocks per SM fit up to L = 128.
+// (NG = 1: the code keeps the notation of an earlier version whose blocks held several groups of 128 threads that
+// screened disjoint level pairs and merged their sets at the end; one group per block and two blocks per SM was faster.)
+template <typename MaskT, bool WIN>
+__global__ void __launch_bounds__(SGT, 2)
 mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const float *__restrict__ padr,
                   unsigned *__restrict__ pass_mask, unsigned long long *__restrict__ stats, int *__restrict__ tile_order,
                   int *__restrict__ bucket_count, unsigned long long *__restrict__ host_word, int epoch) {
+    constexpr int NG = 1;
     extern __shared__ float4 smem4[];
-    float2 *bufs = reinterpret_cast<float2 *>(smem4);                   // [NG groups][Y3 | Z9 | W21]
+    float2 *bufs = reinterpret_cast<float2 *>(smem4);                   // [Y3 | Z9 | W21]
     float *bandL = reinterpret_cast<float *>(bufs + NG * SBUF);         // [SBR][LW]
     float *bandR = bandL + SBR * LW;                                    // [SBR][RW]
     __shared__ __align__(8) uint64_t band_bar;
@@ -185,22 +224,30 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
     const int frame = blockIdx.z, r0 = blockIdx.y * kTileH, c0 = blockIdx.x * BW;
     const int Hd = g.Hd, Wd = g.Wd, L = g.L;
     const int Lp = (L + 1) & ~1, M = Lp >> 1;
-    const int RW = pg.rw;
+    const int RW = WIN ? SWIN : pg.rw;   // pitch of the staged right band
 
     if (tid == 0) {
         mbar_init(&band_bar, 1);
         s_all = 0;
     }
-    if (tid < NG) s_mask[tid] = 0;
+    if (tid < NG) s_mask[tid] = m_zero<MaskT>();
     __syncthreads();
+    const float *sl = padl + ((size_t)frame * pg.rows + r0) * pg.pwl + c0;
+    const float *sr = padr + ((size_t)frame * pg.rows + r0) * pg.pwr + c0;
+    // Window of level pairs [m0, m1): right-band columns Lp-2(m1-1)-2 .. Lp-2 m0+84, from a 16-byte aligned start that
+    // keeps the whole window inside the padded row (pg.rw is a multiple of 4 and >= Lp + 86).
+    auto window_start = [&](int m1) {
+        const int c_lo = (Lp - 2 * (m1 - 1) - 2) & ~3;
+        return c_lo < pg.rw - SWIN ? c_lo : pg.rw - SWIN;
+    };
+    int win0 = WIN ? window_start(M < SWPASS ? M : SWPASS) : 0;
+    if (WIN && win0 < 0) win0 = 0;
     if (tid < 32) {
         if (tid == 0) mbar_expect_tx(&band_bar, (unsigned)(SBR * (LW + RW) * 4));
         __syncwarp();
-        const float *sl = padl + ((size_t)frame * pg.rows + r0) * pg.pwl + c0;
-        const float *sr = padr + ((size_t)frame * pg.rows + r0) * pg.pwr + c0;
         for (int rr = tid; rr < SBR; rr += 32) {
             tma_bulk_g2s(bandL + rr * LW, sl + (size_t)rr * pg.pwl, LW * 4, &band_bar);
-            tma_bulk_g2s(bandR + rr * RW, sr + (size_t)rr * pg.pwr, (unsigned)(RW * 4), &band_bar);
+            tma_bulk_g2s(bandR + rr * RW, sr + (size_t)rr * pg.pwr + win0, (unsigned)(RW * 4), &band_bar);
         }
     }
 
@@ -215,7 +262,7 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
         const bool valid = (r0 + row < Hd) && (c0 + 16 * seg + k < Wd);
         rmax[k] = 0.0f;
         lo[k] = valid ? 0.0f : __int_as_float(0x7f800000);   // pixels outside the image never become candidates
-        cand[k] = 0;
+        cand[k] = m_zero<MaskT>();
     }
 
     {
@@ -226,8 +273,24 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
 
     for (int m = grp; m < M; m += NG) {
         const int d0 = 2 * m;
+        if (WIN && m > 0 && (m % SWPASS) == 0) {
+            // next window: everyone has left phase A of pair m-1 (the group barrier that ended it), so the right band
+            // may be overwritten; the mbarrier's phase flips with every use
+            const int m1 = (m + SWPASS < M) ? m + SWPASS : M;
+            win0 = window_start(m1);
+            if (win0 < 0) win0 = 0;
+            if (tid < 32) {
+                if (tid == 0) mbar_expect_tx(&band_bar, (unsigned)(SBR * RW * 4));
+                __syncwarp();
+                for (int rr = tid; rr < SBR; rr += 32)
+                    tma_bulk_g2s(bandR + rr * RW, sr + (size_t)rr * pg.pwr + win0, (unsigned)(RW * 4), &band_bar);
+            }
+            int spins = 0;
+            while (!mbar_try_wait(&band_bar, (unsigned)((m / SWPASS) & 1)))
+                if (++spins > (1 << 24)) __trap();
+        }
         if (gt < SXW)
-            screen_phase_a(bandL + gt + 4, bandR + gt + (Lp - d0 - 2), RW, bY + gt, bZ + (gt - SZ0), bW + (gt - SW0),
+            screen_phase_a(bandL + gt + 4, bandR + gt + (Lp - d0 - 2 - win0), RW, bY + gt, bZ + (gt - SZ0), bW + (gt - SW0),
                            gt >= SZ0 && gt < SZ1, gt >= SW0 && gt < SW1);
         group_sync(grp);
 
@@ -296,7 +359,7 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
         }
         // ---- candidate bookkeeping: the set always contains every LEVEL within kKeep of the final maximum -----------
         const bool has2 = (d0 + 1 < L);
-        const MaskT bitx = (MaskT)1 << (2 * (m / NG)), bity = bitx << 1;
+        const MaskT bitx = m_bit<MaskT>(2 * (m / NG)), bity = m_bit<MaskT>(2 * (m / NG) + 1);
         float v[16];
         bool hit = false;
 #pragma unroll
@@ -308,14 +371,14 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 if (v[k] >= lo[k]) {
-                    if (v[k] > rmax[k] * kClear) cand[k] = 0;   // everything seen so far is below (1-eps) of the new max
+                    if (v[k] > rmax[k] * kClear) cand[k] = m_zero<MaskT>();   // everything seen so far is below (1-eps) of the new max
                     if (v[k] > rmax[k]) {
                         rmax[k] = v[k];
                         lo[k] = v[k] * kKeep;
                     }
                     // both levels against the UPDATED threshold (<= kKeep * final maximum: still a superset)
-                    if (A[k].x >= lo[k]) cand[k] |= bitx;
-                    if (has2 && A[k].y >= lo[k]) cand[k] |= bity;
+                    if (A[k].x >= lo[k]) m_or(cand[k], bitx);
+                    if (has2 && A[k].y >= lo[k]) m_or(cand[k], bity);
                 }
             }
         }
@@ -328,7 +391,7 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
 #pragma unroll
     for (int k = 0; k < 16; k++) xm[grp * 2048 + k * SGT + gt] = rmax[k];
     __syncthreads();
-    MaskT mine = 0;
+    MaskT mine = m_zero<MaskT>();
     bool weak = false;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
@@ -342,17 +405,13 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
             nan |= (v != v);
             if (og != grp) other = fmaxf(other, v);
         }
-        if (!(other > rmax[k] * kClear)) mine |= cand[k];   // else: none of this group's pairs is within eps of the max
+        if (!(other > rmax[k] * kClear)) m_or(mine, cand[k]);   // else: none of this group's pairs is within eps of the max
         if (nan || !(fmaxf(other, rmax[k]) >= kMinMax)) weak = true;   // the bound does not apply to this pixel
     }
-    if (sizeof(MaskT) == 8)
-        mine = (MaskT)(((unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)((unsigned long long)mine >> 32)) << 32) |
-                       __reduce_or_sync(0xffffffffu, (unsigned)mine));
-    else
-        mine = (MaskT)__reduce_or_sync(0xffffffffu, (unsigned)mine);
+    mine = warp_or(mine);
     weak = __any_sync(0xffffffffu, weak);
     if ((tid & 31) == 0) {
-        if (mine) atomicOr(&s_mask[grp], mine);
+        if (m_any(mine)) shared_or(&s_mask[grp], mine);
         if (weak) atomicOr(&s_all, 1);
     }
     __syncthreads();
@@ -364,7 +423,7 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
             // a candidate level d needs d-1, d, d+1 (circular in L, secondary_matching.cu:28-31) evaluated exactly
             for (int d = 0; d < L; d++) {
                 const int m = d >> 1;
-                if (!((s_mask[m % NG] >> (2 * (m / NG) + (d & 1))) & 1)) continue;
+                if (!m_test(s_mask[m % NG], 2 * (m / NG) + (d & 1))) continue;
                 const int a = ((d + L - 1) % L) >> 1, b = ((d + 1) % L) >> 1;
                 w[m >> 5] |= 1u << (m & 31);
                 w[a >> 5] |= 1u << (a & 31);
@@ -399,16 +458,17 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
     }
 }
 
-template <int NG, typename MaskT>
+template <typename MaskT, bool WIN>
 cudaError_t launch_screen_t(const Geom &g, int frames, const Scratch &s, cudaStream_t st) {
-    const size_t smem = screen_smem_bytes(g.L, g.min_ds, NG);
+    constexpr int NG = 1;
+    const size_t smem = WIN ? screen_smem_bytes_windowed() : screen_smem_bytes(g.L, g.min_ds, NG);
     const PadGeom pg = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
-    cudaError_t e = cudaFuncSetAttribute(mbm_screen_kernel<NG, MaskT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mbm_screen_kernel<MaskT, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(pg.tiles_x, pg.tiles_y, frames);
     e = cudaMemsetAsync(s.bucket_count, 0, kScreenCtrlInts * sizeof(int), st);
     if (e != cudaSuccess) return e;
-    mbm_screen_kernel<NG, MaskT><<<grid, NG * SGT, smem, st>>>(g, pg, s.padl, s.padr, s.pass_mask, s.screen_stats, s.tile_order,
+    mbm_screen_kernel<MaskT, WIN><<<grid, NG * SGT, smem, st>>>(g, pg, s.padl, s.padr, s.pass_mask, s.screen_stats, s.tile_order,
                                                        s.bucket_count, s.screen_host_word, s.range_epoch);
     return cudaGetLastError();
 }
@@ -417,20 +477,17 @@ cudaError_t launch_screen_t(const Geom &g, int frames, const Scratch &s, cudaStr
 
 bool mbm_screen_supported(const Geom &g) {
     const int Lp = (g.L + 1) & ~1;
-    return mbm_wta_fast_supported(g) && Lp / 2 <= 64 && Lp / 2 >= 2 && screen_smem_bytes(g.L, g.min_ds, 2) <= 227 * 1024;
+    return mbm_wta_fast_supported(g) && Lp / 2 <= 64 && Lp / 2 >= 2;
 }
 
 cudaError_t launch_mbm_screen(const Geom &g, int frames, const Scratch &s, cudaStream_t st) {
     if (!mbm_screen_supported(g) || !s.padl || !s.padr || !s.pass_mask || !s.tile_order || !s.bucket_count) return cudaErrorNotSupported;
-    // three groups (12 warps) when their buffers fit next to the row bands and 16 pairs per group suffice, else two
+    // One group of 128 threads per block, two blocks per SM.  L <= 64: the whole right band fits (64-bit candidate sets);
+    // larger L: the right band is staged window by window (128-bit sets).
     const int M = ((g.L + 1) & ~1) / 2;
-    // Best measured: ONE group per block and two blocks per SM (the group sees every pair of its tile, so its running
-    // maxima settle early and there is no cross-group merge) -- possible while 2 x (bands + buffers) fit the SM's shared
-    // memory and 64 bits hold two bits per pair (L <= 64).  Else one block per SM with 3 or 2 groups sharing the bands.
     if (M <= 32 && 2 * (screen_smem_bytes(g.L, g.min_ds, 1) + 1024) <= 227 * 1024)
-        return launch_screen_t<1, unsigned long long>(g, frames, s, st);
-    if (screen_smem_bytes(g.L, g.min_ds, 3) + 1024 <= 227 * 1024 && M <= 48) return launch_screen_t<3, unsigned>(g, frames, s, st);
-    return launch_screen_t<2, unsigned long long>(g, frames, s, st);
+        return launch_screen_t<unsigned long long, false>(g, frames, s, st);
+    return launch_screen_t<Mask128, true>(g, frames, s, st);
 }
 
 }  // namespace sd
