@@ -52,7 +52,7 @@ constexpr int SBR = 54;         // band rows used (32 + 2*10 + 2*1)
 constexpr int SPY = 86, SPZ = 74, SPW = 70;
 constexpr int SZ0 = 6, SZ1 = 78, SW0 = 8, SW1 = 76;
 constexpr int SBUF = 32 * (SPY + SPZ + SPW);   // cells per group
-constexpr int SGT = 128;                       // threads per group
+constexpr int SGT = 128;                       // threads per block
 constexpr float kKeep = 0.998f;             // candidate:  A' >= kKeep * running max        (eps  = 2e-3)
 constexpr float kClear = 1.005f;            // new max > kClear * old max clears the set    (eps' = 5e-3 >= eps/(1-eps))
 constexpr float kMinMax = 32768.0f * 144600.0f * 185910.0f;   // T
@@ -66,8 +66,6 @@ __host__ __device__ inline size_t screen_smem_bytes(int L, int min_ds, int group
 __host__ __device__ inline size_t screen_smem_bytes_windowed() {
     return (size_t)SBUF * sizeof(float2) + (size_t)SBR * (LW + 152) * 4;
 }
-
-__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(SGT) : "memory"); }
 
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 
@@ -204,23 +202,22 @@ constexpr int SWPASS = 32;      // level pairs per window
 // L <= 64, 128 bits up to L = 128.
 // WIN: the right row band is staged one window of SWPASS level pairs at a time (SWIN columns) instead of whole, so the
 // shared-memory footprint does not grow with L and two blocks per SM fit up to L = 128.
-// (NG = 1: the code keeps the notation of an earlier version whose blocks held several groups of 128 threads that
-// screened disjoint level pairs and merged their sets at the end; one group per block and two blocks per SM was faster.)
+// (An earlier version ran several groups of 128 threads per block on disjoint level pairs and merged their sets at the
+// end; one group per block and two blocks per SM was faster: the running maxima see every pair and settle early.)
 template <typename MaskT, bool WIN>
 __global__ void __launch_bounds__(SGT, 2)
 mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const float *__restrict__ padr,
                   unsigned *__restrict__ pass_mask, unsigned long long *__restrict__ stats, int *__restrict__ tile_order,
                   int *__restrict__ bucket_count, unsigned long long *__restrict__ host_word, int epoch) {
-    constexpr int NG = 1;
     extern __shared__ float4 smem4[];
     float2 *bufs = reinterpret_cast<float2 *>(smem4);                   // [Y3 | Z9 | W21]
-    float *bandL = reinterpret_cast<float *>(bufs + NG * SBUF);         // [SBR][LW]
+    float *bandL = reinterpret_cast<float *>(bufs + SBUF);              // [SBR][LW]
     float *bandR = bandL + SBR * LW;                                    // [SBR][RW]
     __shared__ __align__(8) uint64_t band_bar;
-    __shared__ MaskT s_mask[NG];
+    __shared__ MaskT s_mask;
     __shared__ int s_all;
 
-    const int tid = threadIdx.x, grp = tid >> 7, gt = tid & (SGT - 1);
+    const int tid = threadIdx.x, gt = tid;
     const int frame = blockIdx.z, r0 = blockIdx.y * kTileH, c0 = blockIdx.x * BW;
     const int Hd = g.Hd, Wd = g.Wd, L = g.L;
     const int Lp = (L + 1) & ~1, M = Lp >> 1;
@@ -229,8 +226,8 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
     if (tid == 0) {
         mbar_init(&band_bar, 1);
         s_all = 0;
+        s_mask = m_zero<MaskT>();
     }
-    if (tid < NG) s_mask[tid] = m_zero<MaskT>();
     __syncthreads();
     const float *sl = padl + ((size_t)frame * pg.rows + r0) * pg.pwl + c0;
     const float *sr = padr + ((size_t)frame * pg.rows + r0) * pg.pwr + c0;
@@ -251,7 +248,7 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
         }
     }
 
-    float2 *bY = bufs + grp * SBUF, *bZ = bY + 32 * SPY, *bW = bZ + 32 * SPZ;
+    float2 *bY = bufs, *bZ = bY + 32 * SPY, *bW = bZ + 32 * SPZ;
     // phase-B ownership: pooled row `row` of the tile, columns 16*seg .. 16*seg+15 (a warp = one segment: its 32
     // lanes read 32 different rows, conflict-free with the pitches above)
     const int row = gt & 31, seg = gt >> 5;
@@ -271,10 +268,10 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
             if (++spins > (1 << 24)) __trap();  // a lost transaction must not hang the GPU
     }
 
-    for (int m = grp; m < M; m += NG) {
+    for (int m = 0; m < M; m++) {
         const int d0 = 2 * m;
         if (WIN && m > 0 && (m % SWPASS) == 0) {
-            // next window: everyone has left phase A of pair m-1 (the group barrier that ended it), so the right band
+            // next window: everyone has left phase A of pair m-1 (the barrier that ended it), so the right band
             // may be overwritten; the mbarrier's phase flips with every use
             const int m1 = (m + SWPASS < M) ? m + SWPASS : M;
             win0 = window_start(m1);
@@ -292,7 +289,7 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
         if (gt < SXW)
             screen_phase_a(bandL + gt + 4, bandR + gt + (Lp - d0 - 2 - win0), RW, bY + gt, bZ + (gt - SZ0), bW + (gt - SW0),
                            gt >= SZ0 && gt < SZ1, gt >= SW0 && gt < SW1);
-        group_sync(grp);
+        __syncthreads();
 
         // ---- phase B ---------------------------------------------------------------------------------------
         // Sliding sums along the row: the first window is a tree sum, every further output is one dependent add of
@@ -359,7 +356,7 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
         }
         // ---- candidate bookkeeping: the set always contains every LEVEL within kKeep of the final maximum -----------
         const bool has2 = (d0 + 1 < L);
-        const MaskT bitx = m_bit<MaskT>(2 * (m / NG)), bity = m_bit<MaskT>(2 * (m / NG) + 1);
+        const MaskT bitx = m_bit<MaskT>(2 * m), bity = m_bit<MaskT>(2 * m + 1);
         float v[16];
         bool hit = false;
 #pragma unroll
@@ -382,36 +379,23 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
                 }
             }
         }
-        group_sync(grp);   // the buffers are free for the next pass of this group
+        __syncthreads();   // the buffers are free for the next pass
     }
 
-    // ---- merge the groups' candidate sets (they screened disjoint level pairs) -------------------------------------
-    __syncthreads();
-    float *xm = reinterpret_cast<float *>(bufs);   // [NG][16][128] running maxima (lane-contiguous), aliases the idle buffers
-#pragma unroll
-    for (int k = 0; k < 16; k++) xm[grp * 2048 + k * SGT + gt] = rmax[k];
-    __syncthreads();
+    // ---- the tile's set: union over its pixels; pixels the bound does not cover flag everything -----------------------
     MaskT mine = m_zero<MaskT>();
     bool weak = false;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         const bool valid = (r0 + row < Hd) && (c0 + 16 * seg + k < Wd);
         if (!valid) continue;
-        float other = 0.0f;
-        bool nan = false;
-#pragma unroll
-        for (int og = 0; og < NG; og++) {
-            const float v = xm[og * 2048 + k * SGT + gt];
-            nan |= (v != v);
-            if (og != grp) other = fmaxf(other, v);
-        }
-        if (!(other > rmax[k] * kClear)) m_or(mine, cand[k]);   // else: none of this group's pairs is within eps of the max
-        if (nan || !(fmaxf(other, rmax[k]) >= kMinMax)) weak = true;   // the bound does not apply to this pixel
+        m_or(mine, cand[k]);
+        if (!(rmax[k] >= kMinMax)) weak = true;   // below the bound's floor, or NaN
     }
     mine = warp_or(mine);
     weak = __any_sync(0xffffffffu, weak);
     if ((tid & 31) == 0) {
-        if (m_any(mine)) shared_or(&s_mask[grp], mine);
+        if (m_any(mine)) shared_or(&s_mask, mine);
         if (weak) atomicOr(&s_all, 1);
     }
     __syncthreads();
@@ -423,7 +407,7 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
             // a candidate level d needs d-1, d, d+1 (circular in L, secondary_matching.cu:28-31) evaluated exactly
             for (int d = 0; d < L; d++) {
                 const int m = d >> 1;
-                if (!m_test(s_mask[m % NG], 2 * (m / NG) + (d & 1))) continue;
+                if (!m_test(s_mask, d)) continue;
                 const int a = ((d + L - 1) % L) >> 1, b = ((d + 1) % L) >> 1;
                 w[m >> 5] |= 1u << (m & 31);
                 w[a >> 5] |= 1u << (a & 31);
@@ -460,15 +444,14 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
 
 template <typename MaskT, bool WIN>
 cudaError_t launch_screen_t(const Geom &g, int frames, const Scratch &s, cudaStream_t st) {
-    constexpr int NG = 1;
-    const size_t smem = WIN ? screen_smem_bytes_windowed() : screen_smem_bytes(g.L, g.min_ds, NG);
+    const size_t smem = WIN ? screen_smem_bytes_windowed() : screen_smem_bytes(g.L, g.min_ds, 1);
     const PadGeom pg = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
     cudaError_t e = cudaFuncSetAttribute(mbm_screen_kernel<MaskT, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(pg.tiles_x, pg.tiles_y, frames);
     e = cudaMemsetAsync(s.bucket_count, 0, kScreenCtrlInts * sizeof(int), st);
     if (e != cudaSuccess) return e;
-    mbm_screen_kernel<MaskT, WIN><<<grid, NG * SGT, smem, st>>>(g, pg, s.padl, s.padr, s.pass_mask, s.screen_stats, s.tile_order,
+    mbm_screen_kernel<MaskT, WIN><<<grid, SGT, smem, st>>>(g, pg, s.padl, s.padr, s.pass_mask, s.screen_stats, s.tile_order,
                                                        s.bucket_count, s.screen_host_word, s.range_epoch);
     return cudaGetLastError();
 }
