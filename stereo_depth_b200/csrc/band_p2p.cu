@@ -32,7 +32,10 @@ __device__ __forceinline__ bool last_block_done(unsigned *counter, unsigned nblo
     if (threadIdx.x == 0 && threadIdx.y == 0) {
         const unsigned old = atomicAdd(counter, 1u);
         s_last = (old == nblocks - 1) ? 1u : 0u;
-        if (s_last) *counter = 0u;   // ready for the next launch (stream ordered)
+        if (s_last) {
+            __threadfence_system();   // acquire side: everything the other blocks fenced before their increment
+            *counter = 0u;            // ready for the next launch (stream ordered)
+        }
     }
     __syncthreads();
     return s_last != 0u;
