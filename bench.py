@@ -51,7 +51,8 @@ def parse_args():
     p.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     p.add_argument("--frames-per-launch", type=int, default=0, help="0 = library default (fills whole waves of the fused kernel)")
     p.add_argument("--distinct", type=int, default=8, help="distinct synthetic frames generated (tiled to --frames)")
-    p.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / reference_cuda legs")
+    p.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / reference_cuda / natural / multi-GPU legs")
+    p.add_argument("--repeats", type=int, default=5, help="the K-step timed loop is repeated this often; value = median")
     return p.parse_args()
 
 
@@ -167,6 +168,20 @@ def make_inputs(wl, frames, distinct, rank):
     return torch.from_numpy(l), torch.from_numpy(r)
 
 
+def workload_config(args, wl, world):
+    """The workload description both arms print as `config` (identical keys and values: the driver compares them).
+    Everything implementation-specific goes to `impl_config`."""
+    F = args.frames
+    in_bytes = 2 * F * 3 * wl["H"] * wl["W"]
+    return {"workload": f"{args.workload}: {wl['name']}, {F} frames per GPU per step, frame-sharded",
+            "H": wl["H"], "W": wl["W"], "D": wl["D"], "K": wl["K"], "frames_per_gpu_per_step": F,
+            "distinct_frames": max(1, min(args.distinct, F)),
+            "input": "uint8 CHW frames as a camera delivers them (an arm that needs float32 converts with .float(), as "
+                     "cuda_stereo_matching_backend.py:14-15 does)",
+            "l2": f"inputs {in_bytes / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
+            "parallelism": f"frame-batch x{world}, no collective"}
+
+
 def cpu_baseline_leg(wl):
     """Bounded sample: one frame of the workload through the oracle on the host cores."""
     import numpy as np
@@ -183,6 +198,165 @@ def cpu_baseline_leg(wl):
         best = min(best, time.perf_counter() - t)
     return {"value": 1.0 / best, "unit": "frames/s", "cores": O.num_threads(), "kind": "port",
             "sample": f"1 frame of {wl['name']} (best of 2), oracle/stereo_oracle.c with OpenMP over all host cores"}
+
+
+SCREEN_OPS_PER_CELL = 45.0   # lane-ops the level screen executes per (pixel, level) cell (header of csrc/mbm_screen.cu)
+
+
+def copy_ceiling_leg(lh, rh, out_h, steps, world, chunk=8):
+    """The e2e leg's byte pattern with bare cudaMemcpyAsync and NO kernels: per step, every chunk of `chunk` frames
+    is copied host->device (both views) on one stream while a chunk of disparity maps goes device->host on another,
+    all ranks concurrently.  This is what the box's PCIe / host-memory system can carry at this duplex mix."""
+    import torch
+    F = lh.shape[0]
+    dl = torch.empty((chunk,) + tuple(lh.shape[1:]), dtype=lh.dtype, device="cuda")
+    dr = torch.empty_like(dl)
+    do = torch.zeros((chunk,) + tuple(out_h.shape[1:]), dtype=out_h.dtype, device="cuda")
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def step():
+        for f0 in range(0, F, chunk):
+            n = min(chunk, F - f0)
+            with torch.cuda.stream(s_in):
+                dl[:n].copy_(lh[f0:f0 + n], non_blocking=True)
+                dr[:n].copy_(rh[f0:f0 + n], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                out_h[f0:f0 + n].copy_(do[:n], non_blocking=True)
+
+    step()
+    barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0, world)
+    barrier(world)
+    return world * F * steps / dt
+
+
+def natural_leg(args, wl):
+    """The reference's own natural stereo pair (src/python/data/im0.png, im1.png via data/_ref/natural_pair.npz)
+    through the same path, next to the random-dot headline: the level screen's gain is scene dependent."""
+    import numpy as np
+    import torch
+    from stereo_depth_b200 import cuda_depth
+    from stereo_depth_b200.synthetic import load_natural_pair
+    pair = load_natural_pair()
+    if pair is None:
+        return {"unavailable": "data/_ref/natural_pair.npz not present (oracle/make_natural.py needs /root/reference)"}
+    left, right, vmin, vmax = pair
+    H, W = left.shape[1:]
+    F, distinct = 32, 16
+    # 16 distinct frames (the pair rolled horizontally by 8 columns per frame: 199 MB of inputs > L2), tiled to 32
+    ls = np.stack([np.roll(left, 8 * i, axis=2) for i in range(distinct)] * (F // distinct))
+    rs = np.stack([np.roll(right, 8 * i, axis=2) for i in range(distinct)] * (F // distinct))
+    ld, rd = torch.from_numpy(ls).cuda(), torch.from_numpy(rs).cuda()
+    out = torch.empty((F, H, W), dtype=torch.float32, device="cuda")
+    res = {"frames_per_step": F, "distinct_frames": distinct,
+           "data": "the reference's shipped Middlebury-format pair, rolled by 8 columns per frame"}
+    for name, mn, mx in (("headline_range_0_127", 0, wl["D"] - 1), ("reference_default_75_262", vmin, vmax)):
+        sm = cuda_depth.StereoMatching(cuda_depth.StereoMatchingConfiguration(
+            height=H, width=W, downscale_factor=2, min_disparity=mn, max_disparity=mx))
+        one = {"min_disparity": mn, "max_disparity": mx, "levels": sm.dims[2], "screen_active": bool(sm.screen_active)}
+        for screen in ((True, False) if sm.screen_active else (None,)):
+            if screen is not None:
+                sm.set_screen(screen)
+            for _ in range(3):
+                sm.compute_disparity_batch(ld, rd, out=out)
+            sm.screen_stats(reset=True)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                sm.compute_disparity_batch(ld, rd, out=out)
+            e1.record()
+            torch.cuda.synchronize()
+            fps = F * 5 / (e0.elapsed_time(e1) * 1e-3)
+            if screen is None or screen:
+                one.update(fps=round(fps, 1), ms_per_frame=round(1e3 / fps, 4),
+                           evaluated_fraction=round(sm.screen_stats(reset=True), 4), screen_paused=int(sm.screen_paused))
+            else:
+                one.update(fps_screen_off=round(fps, 1), ms_per_frame_screen_off=round(1e3 / fps, 4))
+        res[name] = one
+        del sm
+    return res
+
+
+def c5_leg(world, rank, steps=5):
+    """BASELINE configs[4]: 256 frames of 1280x720 (D=128, K=2), full pipeline, frame-sharded over the GPUs."""
+    import torch
+    from stereo_depth_b200 import cuda_depth
+    from stereo_depth_b200.bands import shard_frames
+    wl = WORKLOADS["C5"]
+    total = 256
+    a, b = shard_frames(total, world, rank)
+    F = b - a
+    ns = argparse.Namespace(distinct=8)
+    lh, rh = make_inputs(wl, F, ns.distinct, rank)
+    ld, rd = lh.cuda(), rh.cuda()
+    sm = cuda_depth.StereoMatching(cuda_depth.StereoMatchingConfiguration(
+        height=wl["H"], width=wl["W"], downscale_factor=wl["K"], min_disparity=0, max_disparity=wl["D"] - 1))
+    out = torch.empty((F, wl["H"], wl["W"]), dtype=torch.float32, device="cuda")
+    for _ in range(3):
+        sm.compute_disparity_batch(ld, rd, out=out)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        sm.compute_disparity_batch(ld, rd, out=out)
+    e1.record()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    return {"fps": round(total * steps / (ms * 1e-3), 1), "frames_total": total, "frames_per_gpu": F, "steps": steps,
+            "workload": wl["name"], "timer": "CUDA events, max over ranks"}
+
+
+def bands_c4_leg(world, rank, steps=20):
+    """BASELINE configs[3]: ONE 3840x2160 frame (D=256, K=2) split into row bands over the GPUs, halos and left-gray rows
+    exchanged through peer memory over NVLink (sd_band_p2p_*).  Checked bit for bit against the single-GPU result."""
+    import torch
+    from stereo_depth_b200 import cuda_depth
+    from stereo_depth_b200.bands import BandedStereoMatching
+    from stereo_depth_b200.synthetic import make_pair
+    H, W, K, D = 2160, 3840, 2, 256
+    left, right, _ = make_pair(H, W, D, seed=1234)
+    kw = dict(height=H, width=W, downscale_factor=K, min_disparity=0, max_disparity=D - 1)
+    sm = BandedStereoMatching(cuda_depth.StereoMatchingConfiguration(**kw), p2p=True)
+    p = sm.plan
+    lb = torch.from_numpy(left[:, p.x0 * K:p.x1 * K].copy()).cuda()
+    rb = torch.from_numpy(right[:, p.x0 * K:p.x1 * K].copy()).cuda()
+    for _ in range(3):
+        out = sm.compute(lb, rb)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = sm.compute(lb, rb)
+    e1.record()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world) / steps
+    full = sm.gather(out)
+    res = None
+    if rank == 0:
+        plain = cuda_depth.StereoMatching(cuda_depth.StereoMatchingConfiguration(**kw), frames_per_launch=1)
+        l, r = torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda()
+        want = plain.compute_disparity_map(l, r)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(5):
+            plain.compute_disparity_map(l, r)
+        s1.record()
+        torch.cuda.synchronize()
+        single = s0.elapsed_time(s1) / 5
+        res = {"ms_per_frame": round(ms, 4), "single_gpu_ms": round(single, 4), "speedup": round(single / ms, 3),
+               "efficiency": round(single / ms / world, 3), "bit_identical": bool(torch.equal(full, want)),
+               "transport": "peer-memory stores + system-scope flags over NVLink (sd_band_p2p_*), no NCCL on the data path",
+               "band_rows": p.band_rows, "halo_rows": p.halo_rows, "level_split": getattr(sm.handle, "level_split", 1),
+               "fused_kernel": sm.handle.active_variant + ("+screen" if sm.handle.screen_active else "")}
+    sm.close()
+    barrier(world)
+    return res
 
 
 def run_ours(args):
@@ -205,23 +379,28 @@ def run_ours(args):
     in_bytes = 2 * F * 3 * H * W
     out_bytes = F * H * W * 4
 
-    # ---- device-resident throughput ----------------------------------------------------------------
+    # ---- device-resident throughput: REPEATS x (exactly K steps), each bracketed by barrier + synchronize; the
+    #      reported value is the median repeat (max over ranks per repeat) -------------------------------------
     for _ in range(max(args.warmup, 3)):
         sm.compute_disparity_batch(ld, rd, out=out_d)
     sampler = ClockSampler(local)
     barrier(world)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier(world)
-    e0.record()
-    for _ in range(args.steps):
-        sm.compute_disparity_batch(ld, rd, out=out_d)
-    e1.record()
-    barrier(world)
-    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    rep_ms = []
+    for _ in range(args.repeats):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(world)
+        e0.record()
+        for _ in range(args.steps):
+            sm.compute_disparity_batch(ld, rd, out=out_d)
+        e1.record()
+        barrier(world)
+        rep_ms.append(max_over_ranks(e0.elapsed_time(e1), world))
     clocks = sampler.stop() if rank == 0 else None
+    ms = statistics.median(rep_ms)
     value = world * F * args.steps / (ms * 1e-3)
+    rep_fps = sorted(world * F * args.steps / (t * 1e-3) for t in rep_ms)
 
     # ---- end to end from pinned host memory through the plugin API ---------------------------------
     for _ in range(2):
@@ -235,6 +414,9 @@ def run_ours(args):
     barrier(world)
     e2e = world * F * args.steps / e2e_s
     same = bool(torch.equal(out_h[:2], out_d[:2].cpu()))
+    keep = out_h[:2].clone()
+    ceiling = copy_ceiling_leg(lh, rh, out_h, max(2, args.steps // 2), world)
+    out_h[:2].copy_(keep)
 
     # ---- single-frame latency through the reference-shaped call (one frame per process() call) --------
     one_l, one_r = lh[0], rh[0]
@@ -264,6 +446,9 @@ def run_ours(args):
     # of a pass may be shorter, so work per launch is the average)
     ops_per_launch = 237.0 * Hd * Wd * L * (2.0 * F / b_n)
     achieved = ops_per_launch / (b_ms / b_n * 1e-3) / 1e12
+    # what the hardware actually executed: the screen's ~45 lane-ops on every cell + 237 on the flagged fraction
+    exec_ops_per_launch = ((SCREEN_OPS_PER_CELL + 237.0 * evaluated_fraction) if screened else 237.0) * Hd * Wd * L * (2.0 * F / b_n)
+    hw_achieved = exec_ops_per_launch / (b_ms / b_n * 1e-3) / 1e12
     kernel_ms = {k: round(v[0] / max(v[1], 1), 4) for k, v in prof.items()}
     total_prof = sum(v[0] for v in prof.values())
     # hardware efficiency of the exact kernel itself: the same launches with the screen switched off (all levels)
@@ -292,22 +477,39 @@ def run_ours(args):
         except (OSError, ValueError):
             traffic = None
 
+    # ---- BASELINE configs[3] and [4]: every rank takes part --------------------------------------------------------
+    multi = {}
+    if not args.no_extras:
+        del ld, rd, out_d, lh, rh, out_h
+        torch.cuda.empty_cache()
+        try:
+            multi["c5"] = c5_leg(world, rank)
+        except Exception as e:  # noqa: BLE001
+            multi["c5"] = {"error": str(e)[:300]}
+        if world > 1:
+            try:
+                multi["bands_c4"] = bands_c4_leg(world, rank)
+            except Exception as e:  # noqa: BLE001
+                multi["bands_c4"] = {"error": str(e)[:300]}
     if rank != 0:
         return
     line = {
         "metric": "frames/s", "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {wl['name']}, {F} frames per GPU per step, frame-sharded",
-                   "H": H, "W": W, "D": D, "K": K, "frames_per_gpu_per_step": F, "input": "uint8 CHW",
-                   "frames_per_launch": frames_per_launch, "fused_kernel_variant": sm.active_variant,
-                   "level_screen": screened, "distinct_frames": min(args.distinct, F),
-                   "l2": f"inputs {in_bytes / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
-                   "parallelism": f"frame-batch x{world}, no collective"},
+        "config": workload_config(args, wl, world),
+        "impl_config": {"frames_per_launch": frames_per_launch, "fused_kernel_variant": sm.active_variant,
+                        "level_screen": screened},
+        "repeats": {"n": args.repeats, "steps_each": args.steps, "value": "median", "fps_min": round(rep_fps[0], 1),
+                    "fps_median": round(value, 1), "fps_max": round(rep_fps[-1], 1),
+                    "timed_seconds_total": round(sum(rep_ms) * 1e-3, 3)},
         "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": out_bytes, "api": "CudaStereoMatchingBackend.process_batch (sd_compute_host)",
                 "timer": "wall clock around the synchronous call, max over ranks", "matches_device_path": same,
-                "single_frame_latency_ms": round(latency_ms, 3)},
+                "single_frame_latency_ms": round(latency_ms, 3),
+                "copy_ceiling_fps": round(ceiling, 1), "frac_of_copy_ceiling": round(e2e / ceiling, 4),
+                "copy_ceiling_how": "the same H2D + D2H bytes per step as bare cudaMemcpyAsync in 8-frame chunks on two "
+                                    "streams, no kernels, all ranks concurrently (wall clock, max over ranks)"},
         "gpu_launches": sm.launches_per_call(F) * args.steps * world,
         "clocks": clocks,
         "roofline": {"bound": "fp32_alu",
@@ -316,6 +518,11 @@ def run_ours(args):
                                 " (fused cost + aggregation + WTA)"),
                      "achieved": round(achieved, 3), "peak": FADD_PEAK_TOPS, "unit": "TFLOP/s",
                      "frac": round(achieved / FADD_PEAK_TOPS, 4), "traffic": traffic,
+                     "traffic_source": "static: one ncu --set full capture (profiles/kernelB_traffic.json), scaled to this launch size; not measured in this run",
+                     "hw_achieved": round(hw_achieved, 3), "hw_frac": round(hw_achieved / FADD_PEAK_TOPS, 4),
+                     "hw_frac_how": "EXECUTED lane-ops (level screen: 45 per cell on every cell + exact kernel: 237 per cell on the "
+                                    "evaluated fraction of the level pairs) / the same time / the same peak; `frac` counts the "
+                                    "ALGORITHMIC 237 per cell",
                      "peak_source": "measured fp32 add peak of the CUDA cores (128 lane-adds/clk/SM x 148 SM x 1.955 GHz, "
                                     "tools/microbench/fadd_bench; MEASURED_PEAKS.json has no ALU figure); 1 lane-op = 1 'FLOP'",
                      "algorithmic_ops_per_launch": ops_per_launch, "frames_per_launch_avg": round(2.0 * F / b_n, 3),
@@ -333,12 +540,19 @@ def run_ours(args):
             # (one --set full capture, profiles/r01_ncu_screen_summary.txt), not measured live
             "screen_kernel": None if screen_ncu is None else dict(screen_ncu, bound="shared-memory crossbar (128 B/clk/SM)",
                                                                  launch_ms=kernel_ms.get("level_screen"))}
+    extra = {}
     if world == 1 and not args.no_extras:
         try:
             line["cpu_baseline"] = cpu_baseline_leg(wl)
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"error": str(e)[:200]}
         line["reference_cuda"] = reference_subprocess(args, frames=4, steps=3)
+        try:
+            extra["natural"] = natural_leg(args, wl)
+        except Exception as e:  # noqa: BLE001
+            extra["natural"] = {"error": str(e)[:300]}
+    extra.update(multi or {})
+    line["extra"] = extra
     print(json.dumps(line), flush=True)
 
 
@@ -366,7 +580,7 @@ def run_reference_gpu(args, wl):
     if mod is None:
         return None
     H, W, K, D = wl["H"], wl["W"], wl["K"], wl["D"]
-    F = min(args.frames, 8)
+    F = args.frames
     torch.cuda.set_device(0)
     lh, rh = make_inputs(wl, F, min(args.distinct, F), 0)
     lh, rh = lh.pin_memory(), rh.pin_memory()
@@ -377,12 +591,13 @@ def run_reference_gpu(args, wl):
     pre_guard = torch.zeros(64 << 20, dtype=torch.uint8, device="cuda")  # noqa: F841  (carved from the cached 2 GiB block)
     sm = mod.StereoMatching(mod.StereoMatchingConfiguration(height=H, width=W, downscale_factor=K, min_disparity=0,
                                                             max_disparity=D - 1))
-    lf = [lh[i].cuda().float().contiguous() for i in range(F)]
-    rf = [rh[i].cuda().float().contiguous() for i in range(F)]
+    nd = max(1, min(args.distinct, F))   # frames repeat with this period: keep one float32 device copy of each
+    lf = [lh[i].cuda().float().contiguous() for i in range(nd)]
+    rf = [rh[i].cuda().float().contiguous() for i in range(nd)]
 
     def step():
         for i in range(F):
-            sm.compute_disparity_map(lf[i], rf[i])
+            sm.compute_disparity_map(lf[i % nd], rf[i % nd])
 
     for _ in range(max(args.warmup, 1)):
         step()
@@ -416,7 +631,7 @@ def run_reference(args):
     base = {"metric": "frames/s", "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
-            "config": {"workload": f"{args.workload}: {wl['name']}", "H": wl["H"], "W": wl["W"], "D": wl["D"], "K": wl["K"]}}
+            "config": workload_config(args, wl, int(os.environ.get("WORLD_SIZE", args.gpus)))}
     res = None
     try:
         import torch
@@ -426,8 +641,9 @@ def run_reference(args):
         base["reference_gpu_error"] = str(e)[:300]
     if res is not None:
         base.update({"value": round(res["value"], 2), "ms_per_step": round(res["ms_per_step"], 3),
-                     "config": dict(base["config"], frames_per_step=res["frames"], input="float32 CHW on device",
-                                    device="the reference's own CUDA kernels on 1 B200 (it has no CPU or multi-GPU path)"),
+                     "impl_config": {"device": "the reference's own CUDA kernels on 1 B200 (it has no CPU or multi-GPU path)",
+                                     "value_input": "float32 CHW on device (what compute_disparity_map accepts)",
+                                     "e2e_input": "uint8 CHW pinned host frames -> .cuda().float().contiguous()"},
                      "cpu_baseline": {"value": round(res["value"], 2), "unit": "frames/s", "cores": 0, "kind": "reference",
                                       "sample": f"{res['frames']} frames per step, reference CUDA kernels (oracle/_ref/cuda_depth.so) "
                                                 "on one B200; cores=0: runs on the GPU, not on host cores"},

@@ -27,7 +27,16 @@ from dataclasses import dataclass
 import torch
 import torch.distributed as dist
 
-HALO_POOLED = 12
+HALO_POOLED = 12   # the halo of the reference's default radii (large_mbm_radius 10, cost radius 1, sad radius 5, K >= 1)
+
+
+def halo_pooled_rows(cfg):
+    """Pooled halo rows a band needs above and below for configuration `cfg` (an sd_config / SdConfig):
+    aggregation (large_mbm_radius) + cost (ncc_patch_radius) + 1 row (top: the row above the band, whose refined
+    disparity the vertical fill reads; bottom: the next row's column 0 read by the horizontal fill), and enough
+    full-resolution rows for the secondary matching window of those rows: halo * K >= K + sad_patch_radius."""
+    K = cfg.downscale_factor
+    return max(cfg.large_mbm_radius + cfg.ncc_patch_radius + 1, -(-(K + cfg.sad_patch_radius) // K))
 
 
 def shard_frames(n_frames, world, rank):
@@ -140,8 +149,9 @@ class BandedStereoMatching:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         g = configuration._as_struct()
-        self.plan = BandPlan.make(g.height, g.width, g.downscale_factor, self.world, self.rank)
-        self.rows_per_rank = [BandPlan.make(g.height, g.width, g.downscale_factor, self.world, r).band_rows
+        halo = halo_pooled_rows(g)   # 12 for the default radii; grows with large_mbm_radius / sad_patch_radius
+        self.plan = BandPlan.make(g.height, g.width, g.downscale_factor, self.world, self.rank, halo)
+        self.rows_per_rank = [BandPlan.make(g.height, g.width, g.downscale_factor, self.world, r, halo).band_rows
                               for r in range(self.world)]
         local = N.SdConfig(*[getattr(g, f) for f in N.CONFIG_FIELDS])
         local.height = self.plan.local_rows
@@ -209,3 +219,14 @@ class BandedStereoMatching:
 
     def gather(self, out_band):
         return gather_rows(out_band, self.rows_per_rank, self.group)
+
+    def close(self):
+        """COLLECTIVE in peer-memory mode: every rank's exported buffer may still be written (halo stores) or read (gray
+        rows) by its neighbours' kernels, so all ranks finish their work and meet at a barrier before anyone frees."""
+        if self.handle is None:
+            return
+        torch.cuda.synchronize()
+        if self.p2p and self._p2p_dtype is not None and self.world > 1 and dist.is_initialized():
+            dist.barrier(group=self.group)
+        self.handle.close()
+        self.handle = None

@@ -19,8 +19,9 @@ def evaluate(disparity_estimate: torch.Tensor, disparity_gt: torch.Tensor, max_d
         raise RuntimeError("disparity_estimate and disparity_gt must be CUDA tensors of the same shape")
     out = torch.empty(4, dtype=torch.float64, device=est.device)
     stream = torch.cuda.current_stream(est.device).cuda_stream
-    _check(N.lib().sd_metrics(est.data_ptr(), gt.data_ptr(), est.numel(), float(max_disparity), float(threshold),
-                              out.data_ptr(), stream), "sd_metrics")
+    with torch.cuda.device(est.device):   # the launch must happen on the tensors' device, whatever is current
+        _check(N.lib().sd_metrics(est.data_ptr(), gt.data_ptr(), est.numel(), float(max_disparity), float(threshold),
+                                  out.data_ptr(), stream), "sd_metrics")
     cnt, d1, th, s = out.tolist()
     if cnt == 0:
         return {"D1": float("nan"), f"Threshold_{int(threshold)}": float("nan"), "MAE": float("nan"), "count": 0}
@@ -37,6 +38,7 @@ def point_cloud(disparity_map: torch.Tensor, focal_length: float, baseline: floa
     xyz = torch.empty((H * W, 3), dtype=torch.float32, device=d.device)
     scratch = torch.empty(nb + 1, dtype=torch.int32, device=d.device)
     stream = torch.cuda.current_stream(d.device).cuda_stream
-    _check(N.lib().sd_point_cloud(d.data_ptr(), H, W, float(baseline) * float(focal_length), float(invalid_disparity),
-                                  xyz.data_ptr(), scratch.data_ptr(), stream), "sd_point_cloud")
+    with torch.cuda.device(d.device):
+        _check(N.lib().sd_point_cloud(d.data_ptr(), H, W, float(baseline) * float(focal_length), float(invalid_disparity),
+                                      xyz.data_ptr(), scratch.data_ptr(), stream), "sd_point_cloud")
     return xyz[: int(scratch[nb].item())]

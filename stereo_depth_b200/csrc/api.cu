@@ -526,6 +526,11 @@ int sd_band_p2p_init(sd_handle *h, int world, int rank, const int32_t *band_row0
         if (rows > tallest) tallest = rows;
     }
     if (halo_rows % K != 0 || band_row0[0] != 0) return fail(h, SD_ERR_SHAPE, "halo must be a multiple of downscale_factor; bands start at row 0");
+    {   // the halo must cover aggregation + cost + 1 pooled rows and the secondary matching window of those rows
+        const int need_a = g.rl + g.r_cost + 1, need_s = (K + g.r_sad + K - 1) / K;
+        if (halo_rows / K < (need_a > need_s ? need_a : need_s))
+            return fail(h, SD_ERR_UNSUPPORTED, "halo too small for this configuration: needs max(large_mbm_radius + ncc_patch_radius + 1, ceil((K + sad_patch_radius) / K)) pooled rows");
+    }
     if (g.H != band_row0[rank + 1] - band_row0[rank] + 2 * halo_rows) return fail(h, SD_ERR_SHAPE, "the handle's height must be band rows + 2 * halo rows");
     DeviceGuard dg(h->device);
     if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
@@ -646,6 +651,17 @@ int sd_compute_host(sd_handle *h, const void *left, const void *right, int dtype
     const int hc = h->chunk < 8 ? h->chunk : 8;
     const int edge = (hc >= 4 && n_frames >= 3 * hc) ? 2 : hc;
     int it = 0;
+    // On any failure below, copies to / from the caller's host buffers may still be in flight: drain before returning.
+    struct Drain {
+        sd_handle *h;
+        bool armed;
+        ~Drain() {
+            if (!armed) return;
+            cudaStreamSynchronize(h->st_h2d);
+            cudaStreamSynchronize(h->st_comp);
+            cudaStreamSynchronize(h->st_d2h);
+        }
+    } drain{h, true};
     for (int f0 = 0; f0 < n_frames; it++) {
         int nf = hc;
         const int left_over = n_frames - f0;
@@ -672,6 +688,7 @@ int sd_compute_host(sd_handle *h, const void *left, const void *right, int dtype
     }
     SD_CUDA(h, cudaStreamSynchronize(h->st_d2h));
     SD_CUDA(h, cudaStreamSynchronize(h->st_comp));
+    drain.armed = false;
     h->ev_last_valid = false;  // everything on this handle has completed
     return SD_OK;
 }
@@ -715,7 +732,7 @@ int sd_get_stage(sd_handle *h, int stage, int frame, float *dst, void *stream) {
         default:
             return fail(h, SD_ERR_SHAPE, "unknown stage");
     }
-    return SD_OK;
+    return mark_last_use(h, st);   // the copy reads scratch: a following call on another stream must wait for it
 }
 
 int sd_set_debug_volumes(sd_handle *h, float *cost_volume, float *aggregated_volume) {

@@ -11,8 +11,9 @@
 //     out = dm' * t > 0 ? (ds + ds')/K : ((dm + dm') + (ds + ds')/K) / 2
 // The parabola's FMA contraction pattern follows the reference's SASS (see oracle/stereo_oracle.c).
 // The aggregated volume is never in HBM: kernel B left (d*, A[d*-1], max A, A[d*+1]) and (A[0], A[L-1]).
-// With min_disparity != 0 the reference indexes the volume with the absolute disparity
-// (secondary_matching.cu:28-31, a bug); we use the relative index (documented deviation).
+// With min_disparity/K != 0 the reference indexes the volume with the ABSOLUTE disparity (secondary_matching.cu:28-31,
+// an upstream bug).  That is reproduced by default (Geom::abs_index, sd_set_compat): the three values are then read
+// through the reference's own pad_index / flat-offset arithmetic; sd_set_compat(h, 0) selects the relative index.
 #include "common.cuh"
 
 namespace sd {

@@ -125,9 +125,14 @@ class StereoMatching:
             if t.dim() != 4 or tuple(t.shape[1:]) != (3, self.height, self.width):
                 raise RuntimeError(f"{name} must have shape [N,3,{self.height},{self.width}], got {list(t.shape)}")
         n = left_images.shape[0]
+        if right_images.shape[0] != n:
+            raise RuntimeError("left and right batches differ in length")
         code = self._dtype_code(left_images, right_images)
         if out is None:
             out = torch.empty((n, self.height, self.width), dtype=torch.float32).pin_memory()
+        elif (not isinstance(out, torch.Tensor) or out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous()
+              or tuple(out.shape) != (n, self.height, self.width)):
+            raise RuntimeError("out must be a contiguous float32 CPU tensor of shape [N,H,W]")
         self._handle.compute_host(left_images.data_ptr(), right_images.data_ptr(), code, n, out.data_ptr())
         return out
 

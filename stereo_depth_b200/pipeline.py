@@ -3,8 +3,11 @@ reference's scripts can run against this backend:
 
   DepthEstimationPipelineConfig / Result / Context / DepthEstimationPipeline
       <- src/python/pipeline/depth_estimation_pipeline.py:14-87
-  run_depth_estimation_pipeline, run_depth_estimation_pipeline_evaluation, reduce_metrics
-      <- src/python/pipeline/depth_estimation_pipeline_runner.py:28-94
+  extract_config_from_camera, validate_pipeline_config_wrt_camera, run_depth_estimation_pipeline,
+  run_depth_estimation_pipeline_evaluation, reduce_metrics
+      <- src/python/pipeline/depth_estimation_pipeline_runner.py:12-94
+  Camera, EvaluationCamera (the protocol the runner consumes; no dataset readers)
+      <- src/python/pipeline/camera/camera.py:7-35
   D1Metric, ThresholdMetric, MAEMetric
       <- src/python/pipeline/depth_estimation_pipeline_metrics.py:18-56 (one fused GPU pass instead of three masked
          tensor expressions: stereo_depth_b200/csrc/consumers.cu)
@@ -15,9 +18,10 @@ user-supplied `right_view_synthesis` object with a `.process(left)` method.
 from __future__ import annotations
 
 import time
+from abc import ABC, abstractmethod
 from contextlib import contextmanager
 from dataclasses import dataclass
-from typing import Any, Dict, Iterable, List, Optional, Tuple
+from typing import Any, Dict, Iterable, Iterator, List, Optional, Tuple
 
 import torch
 
@@ -105,18 +109,78 @@ class DepthEstimationPipeline:
         raise RuntimeError(f"Unsupported stereo matching backend: {self._config.stereo_matching_backend}")
 
 
-def run_depth_estimation_pipeline(image_pairs: Iterable[Tuple[torch.Tensor, torch.Tensor]],
-                                  pipeline: DepthEstimationPipeline, hooks: Iterable = None) -> None:
-    """Frame loop of depth_estimation_pipeline_runner.py:38-66 over any iterable of (left, right) pairs.
-    Hooks are objects with on_pipeline_start() / process(context) / on_pipeline_end()."""
+class Camera(ABC):
+    """camera/camera.py:7-27 -- what the runner needs from an image source."""
+
+    @abstractmethod
+    def focal_length(self) -> float:
+        pass
+
+    @abstractmethod
+    def baseline(self) -> float:
+        pass
+
+    @abstractmethod
+    def get_image_shape(self) -> Tuple[int, int]:
+        pass
+
+    @abstractmethod
+    def get_disparity_boundaries(self) -> Tuple[int, int]:
+        pass
+
+    @abstractmethod
+    def stream_image_pairs(self) -> Iterator[Tuple[torch.Tensor, Optional[torch.Tensor]]]:
+        pass
+
+
+class EvaluationCamera(Camera):
+    """camera/camera.py:30-35."""
+
+    @abstractmethod
+    def stream_image_pairs_with_gt_disparity(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
+        pass
+
+
+def extract_config_from_camera(camera) -> DepthEstimationPipelineConfig:
+    """runner.py:12-19."""
+    min_disparity, max_disparity = camera.get_disparity_boundaries()
+    return DepthEstimationPipelineConfig(image_shape=camera.get_image_shape(), min_disparity=min_disparity,
+                                         max_disparity=max_disparity)
+
+
+def validate_pipeline_config_wrt_camera(config: DepthEstimationPipelineConfig, camera) -> None:
+    """runner.py:22-25 (same comparison, same message)."""
+    if camera.get_image_shape() != config.image_shape:
+        raise RuntimeError(f"Incompatible image shapes between pipeline configuration and camera."
+                           f"Pipeline expects: {config.image_shape} but camera provides: {camera.get_image_shape()}.")
+
+
+def _is_camera(source) -> bool:
+    return hasattr(source, "stream_image_pairs") and hasattr(source, "get_image_shape")
+
+
+def _check_frame_shape(config, left_view) -> None:
+    if tuple(left_view.shape[-2:]) != tuple(config.image_shape):
+        raise RuntimeError(f"Incompatible image shapes between pipeline configuration and camera."
+                           f"Pipeline expects: {config.image_shape} but camera provides: {tuple(left_view.shape[-2:])}.")
+
+
+def run_depth_estimation_pipeline(camera, pipeline: DepthEstimationPipeline, hooks: Iterable = None) -> None:
+    """Frame loop of runner.py:38-66.  `camera` is anything with the reference's Camera protocol (camera/camera.py:7-27:
+    `get_image_shape`, `stream_image_pairs`); a plain iterable of (left, right) pairs is accepted as well.  Hooks are
+    objects with on_pipeline_start() / process(context) / on_pipeline_end() (depth_estimation_pipeline_hooks.py:18-32);
+    they run in order on the calling thread (the reference's joblib pool is clamped to one job, runner.py:47)."""
     hooks = list(hooks or [])
     config = pipeline.get_configuration()
+    if _is_camera(camera):
+        validate_pipeline_config_wrt_camera(config, camera)
+        image_pairs = camera.stream_image_pairs()
+    else:
+        image_pairs = camera
     for hook in hooks:
         hook.on_pipeline_start()
     for frame_index, (left_view, right_view) in enumerate(image_pairs):
-        if tuple(left_view.shape[-2:]) != tuple(config.image_shape):
-            raise RuntimeError(f"Incompatible image shapes between pipeline configuration and camera."
-                               f"Pipeline expects: {config.image_shape} but camera provides: {tuple(left_view.shape[-2:])}.")
+        _check_frame_shape(config, left_view)
         result = pipeline.process(left_view, right_view)
         context = DepthEstimationPipelineContext(disparity_map=result.disparity_map, left_image=result.left_image,
                                                  right_image=result.right_image, config=config, frame_index=frame_index)
@@ -173,22 +237,25 @@ def reduce_metrics(metrics_results: Dict[str, List[float]], reduction: str) -> D
     return {key: ops[reduction](value) for key, value in metrics_results.items()}
 
 
-def run_depth_estimation_pipeline_evaluation(frames_with_gt: Iterable[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]],
-                                             pipeline: DepthEstimationPipeline,
+def run_depth_estimation_pipeline_evaluation(camera, pipeline: DepthEstimationPipeline,
                                              metrics: Iterable[DepthEstimationPipelineMetric] = None,
                                              reduction: str = "mean", verbose: bool = True) -> Dict[str, float]:
-    """Evaluation loop of runner.py:69-94 over any iterable of (left, right, gt_disparity).  D1 / Threshold_n / MAE come
-    from ONE fused pass per frame (consumers.evaluate, mask 0 < gt <= max_disparity); any other metric object is called
+    """Evaluation loop of runner.py:69-94.  `camera` follows the reference's EvaluationCamera protocol
+    (`stream_image_pairs_with_gt_disparity`, camera/camera.py:30-35) or is a plain iterable of (left, right, gt_disparity).
+    D1 / Threshold_n / MAE come from ONE fused pass per frame (consumers.evaluate, mask 0 < gt <= max_disparity); any other metric object is called
     with the reference's (estimate, gt, mask) arguments."""
     from . import consumers
     metrics = list(metrics or [])
     results: Dict[str, List[float]] = {m.name(): [] for m in metrics}
     config = pipeline.get_configuration()
     max_disp = config.max_disparity
+    if hasattr(camera, "stream_image_pairs_with_gt_disparity"):
+        validate_pipeline_config_wrt_camera(config, camera)
+        frames_with_gt = camera.stream_image_pairs_with_gt_disparity()
+    else:
+        frames_with_gt = camera
     for frame_index, (left_view, right_view, gt_disparity) in enumerate(frames_with_gt):
-        if tuple(left_view.shape[-2:]) != tuple(config.image_shape):
-            raise RuntimeError(f"Incompatible image shapes between pipeline configuration and camera."
-                               f"Pipeline expects: {config.image_shape} but camera provides: {tuple(left_view.shape[-2:])}.")
+        _check_frame_shape(config, left_view)
         gt_disparity = gt_disparity.cuda().float()
         result = pipeline.process(left_view, right_view)
         fused: Dict[float, Dict[str, float]] = {}

@@ -49,3 +49,20 @@ def make_batch(n, H, W, D, seed=1234, first_frame=0):
         ls.append(l)
         rs.append(r)
     return np.stack(ls), np.stack(rs)
+
+
+def natural_pair_path():
+    import os
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "_ref", "natural_pair.npz")
+
+
+def load_natural_pair():
+    """The one natural stereo pair the reference ships (src/python/data/im0.png, im1.png, calib.txt: 1920x1080,
+    vmin=75, vmax=262), as extracted by oracle/make_natural.py into the git-ignored data/_ref/.  Returns
+    (left u8 [3,H,W], right u8 [3,H,W], vmin, vmax) or None when the file is not there."""
+    import os
+    p = natural_pair_path()
+    if not os.path.exists(p):
+        return None
+    z = np.load(p)
+    return z["left"], z["right"], int(z["vmin"]), int(z["vmax"])

@@ -61,9 +61,10 @@ def inputs(H, W, D, flavour, seed):
     return left, right
 
 
-def run_case(stages, cuda_depth, name, H, W, K, min_d, max_d, flavour, seed=4242):
-    D = max_d + 1
-    left_u8, right_u8 = inputs(H, W, D, flavour, seed)
+def run_reference(stages, cuda_depth, left_in, right_in, H, W, K, min_d, max_d, keep_volumes=True):
+    """Every intermediate of the reference's own kernels for one pair ([3,H,W] uint8 or float32 numpy arrays):
+    the launchers one by one on tensors carved out of one sentinel-filled pool, then the unmodified public entry
+    point (`out_api`).  Also used live by tests/test_zz_reference_live.py at the BASELINE sizes."""
     Hd, Wd = (H + K - 1) // K, (W + K - 1) // K
     L = max_d // K - min_d // K + 1
     dev = torch.device("cuda")
@@ -81,10 +82,9 @@ def run_case(stages, cuda_depth, name, H, W, K, min_d, max_d, flavour, seed=4242
     cost, agg = views["cost"].view(Hd, Wd, L), views["agg"].view(Hd, Wd, L)
     disp, out = views["disp"].view(Hd, Wd), views["out"].view(H, W)
 
-    left = torch.from_numpy(left_u8).to(dev).float().contiguous()
-    right = torch.from_numpy(right_u8).to(dev).float().contiguous()
-    res = dict(left=left_u8, right=right_u8,
-               config=np.array([H, W, K, min_d, max_d, 1, 5, 5, 1, 4, 10], np.int32))
+    left = torch.from_numpy(np.ascontiguousarray(left_in)).to(dev).float().contiguous()
+    right = torch.from_numpy(np.ascontiguousarray(right_in)).to(dev).float().contiguous()
+    res = {}
     stages.rgb_to_grayscale_inplace(left, gl)
     stages.rgb_to_grayscale_inplace(right, gr)
     stages.mean_pool_inplace(gl, pl, K)
@@ -94,8 +94,9 @@ def run_case(stages, cuda_depth, name, H, W, K, min_d, max_d, flavour, seed=4242
     stages.wta(agg, disp, min_d // K)
     torch.cuda.synchronize()
     res.update(gray_l=gl.cpu().numpy(), gray_r=gr.cpu().numpy(), pool_l=pl.cpu().numpy(),
-               pool_r=pr.cpu().numpy(), cost=cost.cpu().numpy(), agg=agg.cpu().numpy(),
-               wta=disp.cpu().numpy())
+               pool_r=pr.cpu().numpy(), wta=disp.cpu().numpy())
+    if keep_volumes:
+        res.update(cost=cost.cpu().numpy(), agg=agg.cpu().numpy())
     stages.secondary(gl, gr, agg, disp, 5, K)
     torch.cuda.synchronize()
     res["refined"] = disp.cpu().numpy()
@@ -107,14 +108,26 @@ def run_case(stages, cuda_depth, name, H, W, K, min_d, max_d, flavour, seed=4242
     res["out"] = out.cpu().numpy()
 
     # the unmodified public entry point, on the same inputs
+    del views, gl, gr, pl, pr, cost, agg, disp, out, pool
+    torch.cuda.empty_cache()
     big = torch.empty(max(256 << 20, 16 * total), dtype=torch.uint8, device=dev)
     del big  # one large cached segment: device_buffer's tensors are carved from mapped memory
+    pre_guard = torch.zeros(64 << 20, dtype=torch.uint8, device=dev)  # secondary_matching reads rows BEFORE left_grayscaled
     cfg = cuda_depth.StereoMatchingConfiguration(height=H, width=W, downscale_factor=K,
                                                  min_disparity=min_d, max_disparity=max_d)
     sm = cuda_depth.StereoMatching(cfg)
     api = sm.compute_disparity_map(left, right)
     torch.cuda.synchronize()
     res["out_api"] = api.cpu().numpy().copy()
+    del sm, api, pre_guard
+    return res
+
+
+def run_case(stages, cuda_depth, name, H, W, K, min_d, max_d, flavour, seed=4242):
+    left_u8, right_u8 = inputs(H, W, max_d + 1, flavour, seed)
+    res = dict(left=left_u8, right=right_u8,
+               config=np.array([H, W, K, min_d, max_d, 1, 5, 5, 1, 4, 10], np.int32))
+    res.update(run_reference(stages, cuda_depth, left_u8, right_u8, H, W, K, min_d, max_d))
     return res
 
 

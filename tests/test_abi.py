@@ -84,3 +84,39 @@ def test_no_fallback_without_cuda():
     from stereo_depth_b200 import cuda_depth
     with pytest.raises(RuntimeError):
         cuda_depth.StereoMatching(cuda_depth.StereoMatchingConfiguration(height=64, width=64))
+
+
+def test_unmodified_reference_backend_imports_against_the_shim(tmp_path):
+    """src/python/pipeline/depth/cuda_stereo_matching_backend.py, byte for byte, resolves `import cuda_depth` and
+    `from pipeline.depth import StereoMatching` against this package (no GPU needed to import it; running it is the
+    -m gpu test tests/test_zz_reference_live.py::test_unmodified_reference_backend_on_the_shim)."""
+    import torch
+    from test_zz_reference_live import _import_reference_backend
+    from stereo_depth_b200 import backend, cuda_depth
+    mod = _import_reference_backend(tmp_path)
+    assert issubclass(mod.CudaStereoMatchingBackend, backend.StereoMatching)
+    assert mod.cuda_depth is cuda_depth
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            mod.CudaStereoMatchingBackend()
+
+
+def test_runner_protocol_helpers_without_a_gpu():
+    """extract_config_from_camera / validate_pipeline_config_wrt_camera (runner.py:12-25) are host logic."""
+    from stereo_depth_b200 import pipeline as P
+
+    class Cam:
+        def get_image_shape(self):
+            return (375, 1242)
+
+        def get_disparity_boundaries(self):
+            return (1, 64)
+
+    cfg = P.extract_config_from_camera(Cam())
+    assert cfg == P.DepthEstimationPipelineConfig(image_shape=(375, 1242), min_disparity=1, max_disparity=64)
+    P.validate_pipeline_config_wrt_camera(cfg, Cam())
+    with pytest.raises(RuntimeError, match=r"Pipeline expects: \(384, 1280\) but camera provides: \(375, 1242\)"):
+        P.validate_pipeline_config_wrt_camera(P.DepthEstimationPipelineConfig(), Cam())
+    assert issubclass(P.EvaluationCamera, P.Camera)
+    with pytest.raises(TypeError):
+        P.Camera()   # abstract, like the reference's

@@ -43,6 +43,36 @@ def test_banded_world1_equals_plain(K, p2p):
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
+@pytest.mark.parametrize("p2p", [False, True])
+def test_banded_world1_nondefault_radii(p2p):
+    """The band halo is derived from the configuration (bands.halo_pooled_rows): radii larger than the defaults need
+    more than 12 pooled halo rows.  large_mbm_radius 12 + cost radius 2 -> 15 rows; must equal the normal path."""
+    import torch
+    from stereo_depth_b200 import cuda_depth
+    from stereo_depth_b200.bands import BandedStereoMatching, halo_pooled_rows
+    from stereo_depth_b200.synthetic import make_pair
+    H, W, D, K = 144, 256, 32, 2
+    left, right, _ = make_pair(H, W, D, seed=37)
+    kw = dict(height=H, width=W, downscale_factor=K, min_disparity=0, max_disparity=D - 1, ncc_patch_radius=2,
+              sad_patch_radius=7, small_mbm_radius=2, mid_mbm_radius=5, large_mbm_radius=12)
+    cfg = cuda_depth.StereoMatchingConfiguration(**kw)
+    assert halo_pooled_rows(cfg._as_struct()) == 15
+    want = _plain(left, right, kw)
+    sm = BandedStereoMatching(cfg, p2p=p2p)
+    assert sm.plan.halo == 15
+    got = sm.compute(torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda()).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    sm.close()
+    # a halo that is too small for the configuration is refused by the library
+    from stereo_depth_b200 import _native as N
+    local = N.SdConfig(*[getattr(cfg._as_struct(), f) for f in N.CONFIG_FIELDS])
+    local.height = H + 2 * 24
+    h = N.Handle(local, torch.cuda.current_device(), 1)
+    with pytest.raises(RuntimeError, match="halo too small"):
+        h.band_p2p_init(1, 0, [0, H], 24, N.SD_U8)
+    h.close()
+
+
 def _band_worker(rank, world, port, H, W, K, D, outdir):
     import torch
     import torch.distributed as dist
