@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define SD_ABI_VERSION 2   /* 2: level screen, peer-memory row bands, detailed profile read (additions only) */
+#define SD_ABI_VERSION 3   /* 2: level screen, peer-memory row bands, detailed profile read; 3: guard bands (additions only) */
 
 /* Replaces struct stereo_matching_configuration
  * (src/csrc/depth/stereo_matching_configuration.hh:5-17); field order = the pybind ctor's
@@ -126,6 +126,11 @@ int sd_compute_host(sd_handle *h, const void *left, const void *right, int dtype
  * on `cuda_stream`. */
 int sd_get_stage(sd_handle *h, int stage, int frame, float *dst, void *cuda_stream);
 
+/* Zero-copy variant for the stages that live in scratch as plain float planes (gray, pooled, refined): the device
+ * address inside the handle's scratch, valid until the next call that processes a chunk (order your reads after it on
+ * the same stream).  SD_ERR_UNSUPPORTED for SD_STAGE_WTA / SD_STAGE_AGG3 (stored as packed records). */
+int sd_stage_pointer(sd_handle *h, int stage, int frame, const float **ptr);
+
 /* Debug/parity hook: when non-NULL, the fused kernel additionally stores the cost and aggregated
  * volumes ([Hd,Wd,L] floats, d innermost, device memory) of frame 0 of each chunk -- the two
  * tensors the reference materialises (buffer/device_buffer.cc:9-10).  Pass NULLs to switch off. */
@@ -189,6 +194,12 @@ int sd_metrics(const float *disparity, const float *gt_disparity, long long n, f
  * xyz: [H*W,3] floats; scratch: ceil(H*W/1024)+1 ints, the point count is left in scratch[ceil(H*W/1024)]. */
 int sd_point_cloud(const float *disparity, int H, int W, float focal_times_baseline, float invalid_disparity, float *xyz,
                    int *scratch, void *cuda_stream);
+
+/* Debug aid standing in for a memory checker: with SD_DEBUG_GUARDS=1 in the environment at sd_create, every scratch
+ * allocation of the handle is bracketed by 64 KB guard bands holding a known pattern.  sd_check_guards synchronises the
+ * device and returns in *corrupted_bytes how many guard bytes (incl. the slack behind each payload) a stray store has
+ * changed since sd_create.  SD_ERR_UNSUPPORTED when the handle was created without guards. */
+int sd_check_guards(sd_handle *h, long long *corrupted_bytes);
 
 const char *sd_last_error(sd_handle *h);
 int sd_last_cuda_error(sd_handle *h);

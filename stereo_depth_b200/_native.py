@@ -19,7 +19,7 @@ CONFIG_FIELDS = ("height", "width", "downscale_factor", "min_disparity", "max_di
 # every symbol include/stereo_b200.h declares
 EXPORTS = ("sd_abi_version", "sd_config_default", "sd_dims", "sd_create", "sd_destroy", "sd_compute",
            "sd_compute_range", "sd_set_band", "sd_band_p2p_init", "sd_band_p2p_connect", "sd_band_p2p_compute", "sd_compute_host", "sd_get_stage", "sd_set_debug_volumes", "sd_set_compat", "sd_set_variant",
-           "sd_launches_per_call", "sd_frames_per_launch", "sd_active_variant", "sd_set_screen", "sd_screen_active", "sd_screen_stats", "sd_screen_paused", "sd_profile_enable", "sd_profile_read", "sd_profile_read_detail", "sd_metrics", "sd_point_cloud",
+           "sd_launches_per_call", "sd_frames_per_launch", "sd_active_variant", "sd_set_screen", "sd_screen_active", "sd_screen_stats", "sd_screen_paused", "sd_profile_enable", "sd_profile_read", "sd_profile_read_detail", "sd_metrics", "sd_point_cloud", "sd_check_guards", "sd_stage_pointer",
            "sd_last_error", "sd_last_cuda_error")
 
 
@@ -77,6 +77,8 @@ def lib():
     L.sd_profile_read_detail.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.sd_metrics.argtypes = [vp, vp, C.c_longlong, C.c_float, C.c_float, vp, vp]
     L.sd_point_cloud.argtypes = [vp, ip, ip, C.c_float, C.c_float, vp, vp, vp]
+    L.sd_stage_pointer.argtypes = [vp, ip, ip, C.POINTER(vp)]
+    L.sd_check_guards.argtypes = [vp, C.POINTER(C.c_longlong)]
     L.sd_last_error.argtypes = [vp]
     L.sd_last_error.restype = C.c_char_p
     L.sd_last_cuda_error.argtypes = [vp]
@@ -198,6 +200,18 @@ class Handle:
     @property
     def active_variant(self):
         return {1: "generic", 2: "fast", 3: "ws"}.get(lib().sd_active_variant(self._h), "?")
+
+    def stage_pointer(self, stage, frame=0):
+        """Device address of a plain-float scratch plane (gray_l/r, pool_l/r, refined) of the last chunk."""
+        p = C.c_void_p()
+        self.check(lib().sd_stage_pointer(self._h, STAGES[stage], frame, C.byref(p)))
+        return p.value
+
+    def check_guards(self):
+        """Guard-band bytes changed by stray stores (handle created with SD_DEBUG_GUARDS=1); synchronises."""
+        n = C.c_longlong(0)
+        self.check(lib().sd_check_guards(self._h, C.byref(n)))
+        return n.value
 
     def close(self):
         if self._h:

@@ -4,7 +4,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -15,6 +18,8 @@ namespace {
 constexpr int kSlots = 4;  // host pipeline depth (H2D / compute / D2H in flight)
 constexpr double kScreenGiveUp = 0.70;  // evaluated fraction above which the screen costs more than it saves
 constexpr int kScreenPause = 32;        // chunks without the screen before it is probed again
+constexpr size_t kGuardBytes = 64 << 10;  // per side, debug guard bands
+constexpr unsigned char kGuardPattern = 0xA5;
 constexpr int kProfMarks = 7;  // start | gray+pool | plane padding | level screen | cost+agg+WTA | secondary | fill
 }
 
@@ -62,6 +67,10 @@ struct sd_handle {
     // optional per-kernel timing (sd_profile_enable): kProfMarks events per chunk on the launching stream
     bool prof;
     std::vector<cudaEvent_t> *prof_events;
+    // debug guard bands (SD_DEBUG_GUARDS=1 at sd_create): every scratch allocation is bracketed by kGuardBytes of a
+    // known pattern; sd_check_guards counts the bytes a stray store has changed (stands in for compute-sanitizer)
+    bool guards;
+    std::vector<std::pair<char *, size_t>> *guard_allocs;   // (raw base, payload bytes)
     char err[640];
     int last_cuda;
 };
@@ -99,6 +108,33 @@ struct DeviceGuard {
         if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
     }
 };
+
+// Scratch allocation: plain cudaMalloc, or (debug) payload bracketed by two guard bands filled with kGuardPattern.
+cudaError_t scratch_alloc(sd_handle *h, void **p, size_t bytes) {
+    if (!h->guards) return cudaMalloc(p, bytes);
+    const size_t padded = (bytes + 255) & ~(size_t)255;
+    char *raw = nullptr;
+    cudaError_t e = cudaMalloc((void **)&raw, padded + 2 * kGuardBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(raw, kGuardPattern, padded + 2 * kGuardBytes);
+    if (e != cudaSuccess) return e;
+    h->guard_allocs->push_back(std::make_pair(raw, bytes));
+    *p = raw + kGuardBytes;
+    return cudaSuccess;
+}
+
+void scratch_free(sd_handle *h, void *p) {
+    if (!p) return;
+    if (h->guards && h->guard_allocs) {
+        for (auto &a : *h->guard_allocs)
+            if (a.first + kGuardBytes == (char *)p) {
+                cudaFree(a.first);
+                a.first = nullptr;
+                return;
+            }
+    }
+    cudaFree(p);
+}
 
 const char *validate(const sd_config *c) {
     if (c->height <= 0 || c->width <= 0) return "height and width must be positive";
@@ -298,7 +334,12 @@ int sd_create(const sd_config *cfg, int device, int frames_per_launch, sd_handle
     memset(h, 0, sizeof(*h));
     *out = h;  // returned even on failure so the caller can read sd_last_error, then sd_destroy
     h->prof_events = new (std::nothrow) std::vector<cudaEvent_t>();
-    if (!h->prof_events) return fail(h, SD_ERR_NOMEM, "out of host memory");
+    h->guard_allocs = new (std::nothrow) std::vector<std::pair<char *, size_t>>();
+    if (!h->prof_events || !h->guard_allocs) return fail(h, SD_ERR_NOMEM, "out of host memory");
+    {
+        const char *e = getenv("SD_DEBUG_GUARDS");
+        h->guards = e && atoi(e) != 0;
+    }
     h->cfg = *cfg;
     h->device = device;
     if (const char *why = validate(cfg)) return fail(h, SD_ERR_BAD_ARG, why);
@@ -362,22 +403,22 @@ int sd_create(const sd_config *cfg, int device, int frames_per_launch, sd_handle
     if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
     SD_CUDA(h, cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming));
     const size_t F = h->chunk, n = (size_t)g.H * g.W, nd = (size_t)g.Hd * g.Wd;
-    SD_CUDA(h, cudaMalloc((void **)&h->s.gray, F * 2 * n * sizeof(float)));
-    SD_CUDA(h, cudaMalloc((void **)&h->s.pool, F * 2 * nd * sizeof(float)));
-    SD_CUDA(h, cudaMalloc((void **)&h->s.wta4, F * nd * sizeof(float4)));
-    SD_CUDA(h, cudaMalloc((void **)&h->s.edge2, F * nd * sizeof(float2)));
-    SD_CUDA(h, cudaMalloc((void **)&h->s.refined, F * nd * sizeof(float)));
+    SD_CUDA(h, scratch_alloc(h, (void **)&h->s.gray, F * 2 * n * sizeof(float)));
+    SD_CUDA(h, scratch_alloc(h, (void **)&h->s.pool, F * 2 * nd * sizeof(float)));
+    SD_CUDA(h, scratch_alloc(h, (void **)&h->s.wta4, F * nd * sizeof(float4)));
+    SD_CUDA(h, scratch_alloc(h, (void **)&h->s.edge2, F * nd * sizeof(float2)));
+    SD_CUDA(h, scratch_alloc(h, (void **)&h->s.refined, F * nd * sizeof(float)));
     if (mbm_wta_fast_supported(g)) {
         const PadGeom pg = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
-        SD_CUDA(h, cudaMalloc((void **)&h->s.padl, F * (size_t)pg.rows * pg.pwl * sizeof(float)));
-        SD_CUDA(h, cudaMalloc((void **)&h->s.padr, F * (size_t)pg.rows * pg.pwr * sizeof(float)));
-        SD_CUDA(h, cudaMalloc((void **)&h->s.range_flag, sizeof(int)));
+        SD_CUDA(h, scratch_alloc(h, (void **)&h->s.padl, F * (size_t)pg.rows * pg.pwl * sizeof(float)));
+        SD_CUDA(h, scratch_alloc(h, (void **)&h->s.padr, F * (size_t)pg.rows * pg.pwr * sizeof(float)));
+        SD_CUDA(h, scratch_alloc(h, (void **)&h->s.range_flag, sizeof(int)));
         SD_CUDA(h, cudaMemset(h->s.range_flag, 0, sizeof(int)));
         if (mbm_screen_supported(g)) {
-            SD_CUDA(h, cudaMalloc((void **)&h->s.pass_mask, F * (size_t)pg.tiles_x * pg.tiles_y * 4 * sizeof(unsigned)));
-            SD_CUDA(h, cudaMalloc((void **)&h->s.tile_order, F * (size_t)pg.tiles_x * pg.tiles_y * kScreenBuckets * sizeof(int)));
-            SD_CUDA(h, cudaMalloc((void **)&h->s.bucket_count, kScreenCtrlInts * sizeof(int)));
-            SD_CUDA(h, cudaMalloc((void **)&h->s.screen_stats, 2 * sizeof(unsigned long long)));
+            SD_CUDA(h, scratch_alloc(h, (void **)&h->s.pass_mask, F * (size_t)pg.tiles_x * pg.tiles_y * 4 * sizeof(unsigned)));
+            SD_CUDA(h, scratch_alloc(h, (void **)&h->s.tile_order, F * (size_t)pg.tiles_x * pg.tiles_y * kScreenBuckets * sizeof(int)));
+            SD_CUDA(h, scratch_alloc(h, (void **)&h->s.bucket_count, kScreenCtrlInts * sizeof(int)));
+            SD_CUDA(h, scratch_alloc(h, (void **)&h->s.screen_stats, 2 * sizeof(unsigned long long)));
             SD_CUDA(h, cudaMemset(h->s.screen_stats, 0, 2 * sizeof(unsigned long long)));
             SD_CUDA(h, cudaHostAlloc((void **)&h->stats_host, sizeof(unsigned long long), cudaHostAllocMapped));
             *h->stats_host = 0;
@@ -397,9 +438,9 @@ int sd_set_compat(sd_handle *h, int on) {
     if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
     if (on && !h->s.agg_vol) {
         const size_t bytes = (size_t)h->chunk * h->g.Hd * h->g.Wd * h->g.L * sizeof(float);
-        SD_CUDA(h, cudaMalloc((void **)&h->s.agg_vol, bytes));
+        SD_CUDA(h, scratch_alloc(h, (void **)&h->s.agg_vol, bytes));
     } else if (!on && h->s.agg_vol) {
-        SD_CUDA(h, cudaFree(h->s.agg_vol));
+        scratch_free(h, h->s.agg_vol);
         h->s.agg_vol = nullptr;
     }
     h->g.abs_index = on ? 1 : 0;
@@ -411,30 +452,31 @@ int sd_destroy(sd_handle *h) {
     {
         DeviceGuard dg(h->device);
         destroy_host_pipeline(h);
-        cudaFree(h->s.gray);
-        cudaFree(h->s.pool);
-        cudaFree(h->s.wta4);
-        cudaFree(h->s.edge2);
-        cudaFree(h->s.refined);
+        scratch_free(h, h->s.gray);
+        scratch_free(h, h->s.pool);
+        scratch_free(h, h->s.wta4);
+        scratch_free(h, h->s.edge2);
+        scratch_free(h, h->s.refined);
         if (h->ev_last) cudaEventDestroy(h->ev_last);
-        cudaFree(h->s.agg_vol);
-        cudaFree(h->s.padl);
-        cudaFree(h->s.padr);
+        scratch_free(h, h->s.agg_vol);
+        scratch_free(h, h->s.padl);
+        scratch_free(h, h->s.padr);
         if (h->p2p.on) {
             for (int q = 0; q < h->p2p.world; q++)
                 if (q != h->p2p.rank && h->p2p.peer[q]) cudaIpcCloseMemHandle(h->p2p.peer[q]);
             cudaFree(h->p2p.base);
         }
         if (h->stats_host) cudaFreeHost(h->stats_host);
-        cudaFree(h->s.pass_mask);
-        cudaFree(h->s.tile_order);
-        cudaFree(h->s.bucket_count);
-        cudaFree(h->s.screen_stats);
-        cudaFree(h->s.range_flag);
+        scratch_free(h, h->s.pass_mask);
+        scratch_free(h, h->s.tile_order);
+        scratch_free(h, h->s.bucket_count);
+        scratch_free(h, h->s.screen_stats);
+        scratch_free(h, h->s.range_flag);
         if (h->prof_events) {
             for (cudaEvent_t e : *h->prof_events) cudaEventDestroy(e);
             delete h->prof_events;
         }
+        delete h->guard_allocs;
     }
     delete h;
     return SD_OK;
@@ -735,6 +777,23 @@ int sd_get_stage(sd_handle *h, int stage, int frame, float *dst, void *stream) {
     return mark_last_use(h, st);   // the copy reads scratch: a following call on another stream must wait for it
 }
 
+int sd_stage_pointer(sd_handle *h, int stage, int frame, const float **ptr) {
+    if (!h || !ptr) return SD_ERR_BAD_ARG;
+    *ptr = nullptr;
+    if (frame < 0 || frame >= h->chunk) return fail(h, SD_ERR_SHAPE, "frame index outside the chunk");
+    const Geom &g = h->g;
+    const size_t n = (size_t)g.H * g.W, nd = (size_t)g.Hd * g.Wd;
+    switch (stage) {
+        case SD_STAGE_GRAY_L:
+        case SD_STAGE_GRAY_R: *ptr = h->s.gray + ((size_t)frame * 2 + (stage - SD_STAGE_GRAY_L)) * n; break;
+        case SD_STAGE_POOL_L:
+        case SD_STAGE_POOL_R: *ptr = h->s.pool + ((size_t)frame * 2 + (stage - SD_STAGE_POOL_L)) * nd; break;
+        case SD_STAGE_REFINED: *ptr = h->s.refined + frame * nd; break;
+        default: return fail(h, SD_ERR_UNSUPPORTED, "this stage is not stored as a plain float plane (use sd_get_stage)");
+    }
+    return SD_OK;
+}
+
 int sd_set_debug_volumes(sd_handle *h, float *cost_volume, float *aggregated_volume) {
     if (!h) return SD_ERR_BAD_ARG;
     h->dbg_cost = cost_volume;
@@ -837,6 +896,29 @@ int sd_profile_read(sd_handle *h, double *ms, int *launches) {
 int sd_profile_read_detail(sd_handle *h, double *ms, int *launches) {
     if (!h || !ms || !launches) return SD_ERR_BAD_ARG;
     return profile_collect(h, ms, launches);
+}
+
+int sd_check_guards(sd_handle *h, long long *corrupted_bytes) {
+    if (!h || !corrupted_bytes) return SD_ERR_BAD_ARG;
+    *corrupted_bytes = 0;
+    if (!h->guards) return fail(h, SD_ERR_UNSUPPORTED, "guard bands are off: create the handle with SD_DEBUG_GUARDS=1 in the environment");
+    DeviceGuard dg(h->device);
+    if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
+    SD_CUDA(h, cudaDeviceSynchronize());
+    std::vector<unsigned char> host(kGuardBytes + 256);
+    long long bad = 0;
+    for (const auto &a : *h->guard_allocs) {
+        if (!a.first) continue;
+        const size_t padded = (a.second + 255) & ~(size_t)255;
+        // front band; then [payload end, padded end) + back band
+        SD_CUDA(h, cudaMemcpy(host.data(), a.first, kGuardBytes, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < kGuardBytes; i++) bad += host[i] != kGuardPattern;
+        const size_t tail = padded - a.second + kGuardBytes;
+        SD_CUDA(h, cudaMemcpy(host.data(), a.first + kGuardBytes + a.second, tail, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < tail; i++) bad += host[i] != kGuardPattern;
+    }
+    *corrupted_bytes = bad;
+    return SD_OK;
 }
 
 const char *sd_last_error(sd_handle *h) { return h ? h->err : "null handle"; }

@@ -78,3 +78,22 @@ def agg3_from_volume(agg, wta, min_ds=0):
     bd = (wta.astype(np.int64) - min_ds)
     idx = np.stack([(bd - 1) % L, bd % L, (bd + 1) % L], axis=-1)
     return np.take_along_axis(agg, idx, axis=2)
+
+
+def must_flag_fraction(agg, tile_h=32, tile_w=64):
+    """Lower bound of the level screen's `evaluated_fraction` (mbm_screen.cu): whatever its error bound admits, a tile's
+    pass mask has to contain the level PAIRS of every pixel's exact arg-max d* and of d*-1, d*+1 (circular in L,
+    secondary_matching.cu:28-31).  Returns (sum over tiles of those pairs) / (tiles * ceil(L/2)) -- the same ratio
+    sd_screen_stats reports."""
+    Hd, Wd, L = agg.shape
+    M = (L + 1) // 2
+    best = agg.argmax(axis=2)            # first maximum, like the reference's strict '>' scan
+    need = np.zeros((Hd, Wd, M), bool)
+    ii, jj = np.mgrid[0:Hd, 0:Wd]
+    for off in (-1, 0, 1):
+        need[ii, jj, ((best + off) % L) // 2] = True
+    ty, tx = (Hd + tile_h - 1) // tile_h, (Wd + tile_w - 1) // tile_w
+    pad = np.zeros((ty * tile_h, tx * tile_w, M), bool)
+    pad[:Hd, :Wd] = need
+    tiles = pad.reshape(ty, tile_h, tx, tile_w, M).any(axis=(1, 3))
+    return float(tiles.sum()) / float(ty * tx * M)

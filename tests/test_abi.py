@@ -17,7 +17,7 @@ def test_library_exports_every_declared_symbol():
     lib = N.lib()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.sd_abi_version() == 2
+    assert lib.sd_abi_version() == 3
 
 
 def test_config_defaults_match_reference_struct():
