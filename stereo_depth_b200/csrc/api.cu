@@ -33,6 +33,7 @@ struct sd_handle {
     int sms, per_sm_fast;  // SM count and resident blocks per SM of the specialised kernel (launch cost models)
     bool screen;     // certified level screen in front of the specialised kernel (default on where supported)
     int epoch;       // chunk counter, tags the out-of-range flag of the screen
+    int abs_mode;    // layout of Scratch::agg_vol for the chunk in flight: 0 none, 1 whole volume, 2 compact (gather pass)
     // Adaptive policy: the screen only pays off when it removes work.  The last block of every screen launch posts
     // {chunk tag, pairs screened, pairs flagged} as one 64-bit store to mapped host memory (no copy, no wait); the
     // next chunks look at the latest word that has arrived: if the fused kernel still had to evaluate more than
@@ -193,9 +194,11 @@ int prof_mark(sd_handle *h, cudaStream_t st) {
 
 // The level screen runs in front of the specialised kernel only: not in the debug / reference-compat modes (they need
 // every level of the volume) and not with an explicitly selected generic or warp-specialised variant.
+// In reference-compat mode (absolute-index reads, Scratch::agg_vol) the screen stays on: instead of the whole volume, a
+// gather pass then evaluates just the level pairs those reads ask for (Geom::abs_index == 2, see run_chunk).
 bool screen_allowed(const sd_handle *h) {
     return h->screen && h->s.pass_mask && h->s.padl && (h->variant == 0 || h->variant == 2) && !h->dbg_cost &&
-           !h->dbg_agg && !h->s.agg_vol && mbm_screen_supported(h->g);
+           !h->dbg_agg && (!h->s.agg_vol || h->s.gather_mask) && mbm_screen_supported(h->g);
 }
 
 // Does the screen pay for a launch of `frames` frames?  Behind the screen a launch cannot finish before its heaviest
@@ -230,7 +233,6 @@ int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int 
     if (k0 <= 0 && 0 <= k1) SD_CUDA(h, launch_gray_pool(h->g, left, right, dtype, frames, h->s, st));
     if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
     if (k0 <= 1 && 1 <= k1) {
-        // (reference-compat mode: the kernels also materialise the aggregated volume into h->s.agg_vol)
         h->s.range_epoch = ++h->epoch;
         const int v = active_variant(h, frames);
         bool screen = (v == 2) && screen_active(h, frames);
@@ -246,16 +248,32 @@ int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int 
                 screen = false;
             }
         }
+        // Reference-compat mode (min_disparity/K != 0): secondary matching reads the aggregated volume at ABSOLUTE
+        // indices.  Without the screen the fused kernel evaluates every level anyway and stores the whole volume
+        // (abs_index 1).  Behind the screen it does not: WTA first (no store), then a gather pass of the same kernel over
+        // exactly the level pairs those reads will touch, into a compact per-tile volume (abs_index 2).
+        const bool gather = screen && h->s.agg_vol != nullptr;
+        h->abs_mode = h->s.agg_vol ? (gather ? 2 : 1) : 0;
         if (v == 2) SD_CUDA(h, launch_pad_pooled(h->g, frames, h->s, st));
         if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
         if (screen) SD_CUDA(h, launch_mbm_screen(h->g, frames, h->s, st));
         if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
         if (v == 3) SD_CUDA(h, launch_mbm_wta_ws(h->g, frames, h->s, st));   // (pads its planes itself)
-        else if (v == 2) SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st, screen));
+        else if (v == 2 && gather) {
+            Scratch wta_only = h->s;
+            wta_only.agg_vol = nullptr;
+            SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, wta_only, nullptr, nullptr, st, true));
+            SD_CUDA(h, launch_abs_targets(h->g, frames, h->s, st));
+            SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, nullptr, nullptr, st, false, true));
+        } else if (v == 2) SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st, screen));
         else SD_CUDA(h, launch_mbm_wta_generic(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
     }
     if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
-    if (k0 <= 2 && 2 <= k1) SD_CUDA(h, launch_secondary(h->g, frames, h->s, st));
+    if (k0 <= 2 && 2 <= k1) {
+        Geom g2 = h->g;
+        g2.abs_index = h->abs_mode;   // which layout Scratch::agg_vol holds for THIS chunk
+        SD_CUDA(h, launch_secondary(g2, frames, h->s, st));
+    }
     if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
     if (k0 <= 3 && 3 <= k1) SD_CUDA(h, launch_fill(h->g, frames, h->s, h->gv, out, st));
     if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
@@ -416,6 +434,7 @@ int sd_create(const sd_config *cfg, int device, int frames_per_launch, sd_handle
         SD_CUDA(h, cudaMemset(h->s.range_flag, 0, sizeof(int)));
         if (mbm_screen_supported(g)) {
             SD_CUDA(h, scratch_alloc(h, (void **)&h->s.pass_mask, F * (size_t)pg.tiles_x * pg.tiles_y * 4 * sizeof(unsigned)));
+            SD_CUDA(h, scratch_alloc(h, (void **)&h->s.gather_mask, F * (size_t)pg.tiles_x * pg.tiles_y * 4 * sizeof(unsigned)));
             SD_CUDA(h, scratch_alloc(h, (void **)&h->s.tile_order, F * (size_t)pg.tiles_x * pg.tiles_y * kScreenBuckets * sizeof(int)));
             SD_CUDA(h, scratch_alloc(h, (void **)&h->s.bucket_count, kScreenCtrlInts * sizeof(int)));
             SD_CUDA(h, scratch_alloc(h, (void **)&h->s.screen_stats, 2 * sizeof(unsigned long long)));
@@ -437,8 +456,10 @@ int sd_set_compat(sd_handle *h, int on) {
     DeviceGuard dg(h->device);
     if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
     if (on && !h->s.agg_vol) {
-        const size_t bytes = (size_t)h->chunk * h->g.Hd * h->g.Wd * h->g.L * sizeof(float);
-        SD_CUDA(h, scratch_alloc(h, (void **)&h->s.agg_vol, bytes));
+        // sized for both layouts: the whole volume [L][Hd*Wd] and the compact per-tile one of the gather pass
+        size_t per_frame = (size_t)h->g.Hd * h->g.Wd * h->g.L;
+        if (h->s.gather_mask && compact_volume_floats(h->g) > per_frame) per_frame = compact_volume_floats(h->g);
+        SD_CUDA(h, scratch_alloc(h, (void **)&h->s.agg_vol, (size_t)h->chunk * per_frame * sizeof(float)));
     } else if (!on && h->s.agg_vol) {
         scratch_free(h, h->s.agg_vol);
         h->s.agg_vol = nullptr;
@@ -468,6 +489,7 @@ int sd_destroy(sd_handle *h) {
         }
         if (h->stats_host) cudaFreeHost(h->stats_host);
         scratch_free(h, h->s.pass_mask);
+        scratch_free(h, h->s.gather_mask);
         scratch_free(h, h->s.tile_order);
         scratch_free(h, h->s.bucket_count);
         scratch_free(h, h->s.screen_stats);
@@ -819,7 +841,9 @@ int sd_launches_per_call(sd_handle *h, int n_frames) {
     const int nchunks = (n_frames + h->chunk - 1) / h->chunk, base = n_frames / nchunks, extra = n_frames % nchunks;
     for (int c = 0; c < nchunks; c++) {   // the same split as sd_compute
         const int nf = base + (c < extra ? 1 : 0);
-        total += 4 + (active_variant(h, nf) >= 2 ? 1 : 0) + (active_variant(h, nf) == 2 && screen_active(h, nf) ? 1 : 0);
+        const bool scr = active_variant(h, nf) == 2 && screen_active(h, nf);
+        // (+2 behind the screen in reference-compat mode: absolute-index targets + gather pass)
+        total += 4 + (active_variant(h, nf) >= 2 ? 1 : 0) + (scr ? 1 : 0) + (scr && h->s.agg_vol ? 2 : 0);
     }
     return total;
 }

@@ -41,8 +41,11 @@ struct Geom {
     // the global image.  band_x_off = global pooled row of local pooled row 0 (may be negative: circular),
     // Hd_glob / H_glob = global heights.  Normal mode: 0, Hd, H.
     int band_x_off, Hd_glob, H_glob;
-    // 1: secondary matching indexes the aggregated volume with the ABSOLUTE disparity, like the reference
-    // (secondary_matching.cu:28-31).  Needs Scratch::agg_vol.  Default when min_disparity/K != 0.
+    // != 0: secondary matching indexes the aggregated volume with the ABSOLUTE disparity, like the reference
+    // (secondary_matching.cu:28-31).  Default when min_disparity/K != 0.  Needs Scratch::agg_vol, which holds
+    //   1: the whole volume, plane-major [F][L][Hd*Wd]  (written by the fused kernel while it evaluates every level)
+    //   2: only the level pairs some pixel's absolute-index read asks for, per 32x64 tile:
+    //      [F*tiles][rank of the pair in Scratch::gather_mask][level parity][32*64]  (gather pass, api.cu run_chunk)
     int abs_index;
 };
 
@@ -93,6 +96,8 @@ struct Scratch {
     float *padl, *padr;  // [F][rows][pwl], [F][rows][pwr] wrap-padded pooled planes (PadGeom), NULL if unsupported
     // Certified level screen (mbm_screen.cu), all NULL when unsupported:
     unsigned *pass_mask;              // [F][tiles_y][tiles_x][4] bit m = the fused kernel must run level pair m of that tile
+    unsigned *gather_mask;            // same shape: level pairs whose aggregated values the absolute-index reads of
+                                      // secondary matching need (reference-compat mode behind the screen), else NULL
     int *tile_order;                  // [kScreenBuckets][F*tiles] tile ids bucketed by flagged-pair count (heaviest bucket last)
     int *bucket_count;                // [kScreenCtrlInts] tiles per bucket + per-chunk counters (zeroed before every screen launch)
     unsigned long long *screen_host_word;  // device alias of a mapped host word: per-chunk screen outcome, or NULL
@@ -119,8 +124,17 @@ cudaError_t launch_mbm_wta_generic(const Geom &g, int frames, const Scratch &s, 
                                    float *dbg_agg, cudaStream_t st);
 bool mbm_wta_fast_supported(const Geom &g);
 // use_screen: run only the level pairs flagged in s.pass_mask (written by launch_mbm_screen for the same chunk)
+// gather: no WTA; evaluate the level pairs flagged in s.gather_mask and store their aggregated values into s.agg_vol
+// in the compact per-tile layout (Geom::abs_index == 2)
 cudaError_t launch_mbm_wta_fast(const Geom &g, int frames, const Scratch &s, float *dbg_cost,
-                                float *dbg_agg, cudaStream_t st, bool use_screen = false);
+                                float *dbg_agg, cudaStream_t st, bool use_screen = false, bool gather = false);
+// marks in s.gather_mask (zeroed by the caller) the level pairs the absolute-index reads of secondary matching need
+cudaError_t launch_abs_targets(const Geom &g, int frames, const Scratch &s, cudaStream_t st);
+// floats per frame of the compact layout (>= Hd*Wd*L)
+inline size_t compact_volume_floats(const Geom &g) {
+    const PadGeom pg = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
+    return (size_t)pg.tiles_x * pg.tiles_y * (((size_t)g.L + 1) / 2) * 2 * kTileH * kTileW;
+}
 bool mbm_screen_supported(const Geom &g);
 cudaError_t launch_mbm_screen(const Geom &g, int frames, const Scratch &s, cudaStream_t st);
 bool mbm_wta_ws_supported(const Geom &g);

@@ -51,7 +51,9 @@ __host__ __device__ inline size_t smem_bytes(int L, int min_ds) {
     return (size_t)Cfg<BH>::PRW * NCHUNK * 16 + (size_t)Cfg<BH>::BR * (LW + make_pad_geom(64, 64, L, min_ds).rw) * 4;
 }
 
-template <int BH, bool DBG, int MODE, bool STORE>
+// STORE: 0 nothing, 1 the whole aggregated volume (plane-major), 2 GATHER: no WTA at all, the flagged pairs' values go
+// to the compact per-tile volume (Geom::abs_index == 2) and wta4 / edge2 are left untouched.
+template <int BH, bool DBG, int MODE, int STORE>
 __global__ void __launch_bounds__(Cfg<BH>::NT, (BH <= 32) ? 2 : 1)
 mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const float *__restrict__ padr,
                     float4 *__restrict__ wta4, float2 *__restrict__ edge2, float *__restrict__ dbg_cost,
@@ -103,7 +105,8 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
     if (tid == 0) mbar_init(&band_bar, 1);
     if (tid < 4) {
         unsigned w = 0xffffffffu;
-        if (pass_mask && *range_flag != range_epoch)
+        // (gather pass: the masks are exact requests, not a screen result -- they hold whatever the range flag says)
+        if (pass_mask && (STORE == 2 || *range_flag != range_epoch))
             w = pass_mask[(size_t)tile * 4 + tid];
         s_pass[tid] = w;
     }
@@ -380,7 +383,22 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
                 }
             }
         }
-        if (STORE && agg_planes) {
+        if (STORE == 2) {
+            // gather pass: pair m is the rank-th flagged pair of this tile; its two levels go to
+            // agg_planes[tile][rank][level parity][32*64] -- one coalesced 16-byte store per thread row and level
+            int rank = __popc(s_pass[m >> 5] & ((1u << (m & 31)) - 1u));
+            for (int w = 0; w < (m >> 5); w++) rank += __popc(s_pass[w]);
+            float *q0 = agg_planes + ((size_t)tile * M + rank) * (2 * BH * BW) + (4 * ty) * BW + 4 * tx;
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                *reinterpret_cast<float4 *>(q0 + a * BW) = make_float4(hv[a * 4].x, hv[a * 4 + 1].x, hv[a * 4 + 2].x, hv[a * 4 + 3].x);
+                *reinterpret_cast<float4 *>(q0 + a * BW + BH * BW) =
+                    make_float4(hv[a * 4].y, hv[a * 4 + 1].y, hv[a * 4 + 2].y, hv[a * 4 + 3].y);
+            }
+            __syncthreads();  // everyone is done reading the plane before the next pass overwrites it
+            continue;
+        }
+        if (STORE == 1 && agg_planes) {
             // reference-compat mode: materialise the aggregated volume, plane-major [F][L][Hd*Wd] so that the 4
             // pixels of a thread row are one coalesced 16-byte store per level
             float *pl0 = agg_planes + ((size_t)frame * L + d0) * np + (size_t)px0 * Wd + py0;
@@ -438,6 +456,7 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
         __syncthreads();  // everyone is done reading the plane before the next pass overwrites it
     }
 
+    if (STORE == 2) return;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         const int x = px0 + (k >> 2), y = py0 + (k & 3);
@@ -445,7 +464,7 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
     }
 }
 
-template <int BH, bool DBG, int MODE, bool STORE>
+template <int BH, bool DBG, int MODE, int STORE>
 cudaError_t launch_t(const Geom &g, int frames, const Scratch &s, float *dbg_cost, float *dbg_agg, cudaStream_t st,
                      bool use_screen = false) {
     const size_t smem = smem_bytes<BH>(g.L, g.min_ds);
@@ -454,6 +473,12 @@ cudaError_t launch_t(const Geom &g, int frames, const Scratch &s, float *dbg_cos
     cudaError_t e = cudaFuncSetAttribute(mbm_wta_fast_kernel<BH, DBG, MODE, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((g.Wd + BW - 1) / BW, (g.Hd + BH - 1) / BH, frames);
+    if (STORE == 2) {
+        mbm_wta_fast_kernel<BH, DBG, MODE, STORE><<<grid, Cfg<BH>::NT, smem, st>>>(
+            g, pg, s.padl, s.padr, s.wta4, s.edge2, nullptr, nullptr, s.agg_vol, s.gather_mask, s.range_flag, s.range_epoch,
+            nullptr, s.bucket_count);
+        return cudaGetLastError();
+    }
     mbm_wta_fast_kernel<BH, DBG, MODE, STORE><<<grid, Cfg<BH>::NT, smem, st>>>(
         g, pg, s.padl, s.padr, s.wta4, s.edge2, dbg_cost, dbg_agg, s.agg_vol, use_screen ? s.pass_mask : nullptr,
         s.range_flag, s.range_epoch, use_screen ? s.tile_order : nullptr, s.bucket_count);
@@ -481,15 +506,19 @@ bool mbm_wta_fast_supported(const Geom &g) {
 // The wrap-padded planes (launch_pad_pooled) and, with use_screen, the pass masks of this chunk (launch_mbm_screen)
 // must already be in flight on `st`.
 cudaError_t launch_mbm_wta_fast(const Geom &g, int frames, const Scratch &s, float *dbg_cost, float *dbg_agg,
-                                cudaStream_t st, bool use_screen) {
+                                cudaStream_t st, bool use_screen, bool gather) {
     if (!mbm_wta_fast_supported(g) || !s.padl || !s.padr) return cudaErrorNotSupported;
-    // the debug / reference-compat modes need every level of the volume: no screen there
-    if (dbg_cost || dbg_agg) return launch_t<32, true, 0, true>(g, frames, s, dbg_cost, dbg_agg, st);
-    if (s.agg_vol) return launch_t<32, false, 2, true>(g, frames, s, nullptr, nullptr, st);
+    if (gather) {
+        if (!s.agg_vol || !s.gather_mask) return cudaErrorNotSupported;
+        return launch_t<32, false, 2, 2>(g, frames, s, nullptr, nullptr, st);
+    }
+    // the debug / whole-volume modes need every level: no screen there
+    if (dbg_cost || dbg_agg) return launch_t<32, true, 0, 1>(g, frames, s, dbg_cost, dbg_agg, st);
+    if (s.agg_vol) return launch_t<32, false, 2, 1>(g, frames, s, nullptr, nullptr, st);
     switch (fast_mode()) {
-        case 1: return launch_t<32, false, 1, false>(g, frames, s, nullptr, nullptr, st, use_screen);
-        case 2: return launch_t<32, false, 2, false>(g, frames, s, nullptr, nullptr, st, use_screen);
-        default: return launch_t<32, false, 0, false>(g, frames, s, nullptr, nullptr, st, use_screen);
+        case 1: return launch_t<32, false, 1, 0>(g, frames, s, nullptr, nullptr, st, use_screen);
+        case 2: return launch_t<32, false, 2, 0>(g, frames, s, nullptr, nullptr, st, use_screen);
+        default: return launch_t<32, false, 0, 0>(g, frames, s, nullptr, nullptr, st, use_screen);
     }
 }
 

@@ -39,6 +39,7 @@ template <int KT>
 __global__ void __launch_bounds__(128) secondary_kernel(Geom g, const float *__restrict__ gray,
                                                         const float4 *__restrict__ wta4,
                                                         const float2 *__restrict__ edge2, const float *__restrict__ agg_vol,
+                                                        const unsigned *__restrict__ gather_mask, PadGeom pg,
                                                         float *__restrict__ refined) {
     const int y = blockIdx.x * blockDim.x + threadIdx.x;
     const int x = blockIdx.y * blockDim.y + threadIdx.y;
@@ -262,7 +263,19 @@ __global__ void __launch_bounds__(128) secondary_kernel(Geom g, const float *__r
             auto rd = [&](int q, float safe) {
                 const long long flat = po + ref_pad_index(q, g.L);     // index into the reference's [Hd][Wd][L] tensor
                 if (flat < 0) return safe;                             // before the tensor: SAFE (relative) value
-                return __ldg(vol + (size_t)(flat % g.L) * npix + (size_t)(flat / g.L));
+                const int lv = (int)(flat % g.L);
+                const long long sp = flat / g.L;                       // source pixel (this one, or an earlier one)
+                if (g.abs_index == 2) {
+                    // compact volume of the gather pass: [F*tiles][rank of the pair in the tile's mask][parity][32*64]
+                    const int sx = (int)(sp / g.Wd), sy = (int)(sp % g.Wd), m = lv >> 1, M = (g.L + 1) >> 1;
+                    const size_t tile = ((size_t)frame * pg.tiles_y + sx / kTileH) * pg.tiles_x + sy / kTileW;
+                    const unsigned *mk = gather_mask + tile * 4;
+                    int rank = __popc(__ldg(mk + (m >> 5)) & ((1u << (m & 31)) - 1u));
+                    for (int w = 0; w < (m >> 5); w++) rank += __popc(__ldg(mk + w));
+                    return __ldg(agg_vol + (tile * M + rank) * (size_t)(2 * kTileH * kTileW) + (size_t)(lv & 1) * (kTileH * kTileW) +
+                                 (sx % kTileH) * kTileW + (sy % kTileW));
+                }
+                return __ldg(vol + (size_t)lv * npix + (size_t)sp);
             };
             a_d = rd(dm, a_d);
             a_p1 = rd(dm + 1, a_p1);
@@ -281,16 +294,53 @@ __global__ void __launch_bounds__(128) secondary_kernel(Geom g, const float *__r
     refined[o] = result;
 }
 
+// Which aggregated values will secondary matching's absolute-index reads touch?  One thread per pooled pixel: the
+// three reads agg[x][y][pad_index(dm + {0, +1, -1}, L)] of secondary_matching.cu:28-31 (flat addressing: a negative
+// pad_index lands in an earlier pixel), each marked as a level pair in the mask of the 32x64 tile that holds the SOURCE
+// pixel.  The gather pass of the fused kernel then evaluates exactly those pairs.  (Every pixel is marked: whether its
+// refinement branch is taken is only known once secondary matching has run.)
+__global__ void abs_targets_kernel(Geom g, PadGeom pg, const float4 *__restrict__ wta4, unsigned *__restrict__ gather_mask) {
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x = blockIdx.y * blockDim.y + threadIdx.y;
+    const int frame = blockIdx.z;
+    if (x >= g.Hd || y >= g.Wd) return;
+    const size_t o = (size_t)frame * g.Hd * g.Wd + (size_t)x * g.Wd + y;
+    const int dm = (int)__fadd_rn(wta4[o].x, (float)g.min_ds);
+    const long long po = ((long long)x * g.Wd + y) * g.L;
+#pragma unroll
+    for (int k = -1; k <= 1; k++) {
+        const long long flat = po + ref_pad_index(dm + k, g.L);
+        if (flat < 0) continue;
+        const int lv = (int)(flat % g.L), m = lv >> 1;
+        const long long sp = flat / g.L;
+        const int sx = (int)(sp / g.Wd), sy = (int)(sp % g.Wd);
+        unsigned *w = gather_mask + (((size_t)frame * pg.tiles_y + sx / kTileH) * pg.tiles_x + sy / kTileW) * 4 + (m >> 5);
+        const unsigned bit = 1u << (m & 31);
+        if (!(*reinterpret_cast<volatile unsigned *>(w) & bit)) atomicOr(w, bit);   // mostly already set by a neighbour
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_abs_targets(const Geom &g, int frames, const Scratch &s, cudaStream_t st) {
+    if (!s.gather_mask) return cudaErrorNotSupported;
+    const PadGeom pg = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
+    cudaError_t e = cudaMemsetAsync(s.gather_mask, 0, (size_t)frames * pg.tiles_x * pg.tiles_y * 4 * sizeof(unsigned), st);
+    if (e != cudaSuccess) return e;
+    dim3 block(32, 8), grid((g.Wd + 31) / 32, (g.Hd + 7) / 8, frames);
+    abs_targets_kernel<<<grid, block, 0, st>>>(g, pg, s.wta4, s.gather_mask);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_secondary(const Geom &g, int frames, const Scratch &s, cudaStream_t st) {
     dim3 block(32, 4), grid((g.Wd + 31) / 32, (g.Hd + 3) / 4, frames);
+    const PadGeom pg = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
     switch (g.K) {
-        case 1: secondary_kernel<1><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.agg_vol, s.refined); break;
-        case 2: secondary_kernel<2><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.agg_vol, s.refined); break;
-        case 3: secondary_kernel<3><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.agg_vol, s.refined); break;
-        case 4: secondary_kernel<4><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.agg_vol, s.refined); break;
-        default: secondary_kernel<0><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.agg_vol, s.refined); break;
+        case 1: secondary_kernel<1><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.agg_vol, s.gather_mask, pg, s.refined); break;
+        case 2: secondary_kernel<2><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.agg_vol, s.gather_mask, pg, s.refined); break;
+        case 3: secondary_kernel<3><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.agg_vol, s.gather_mask, pg, s.refined); break;
+        case 4: secondary_kernel<4><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.agg_vol, s.gather_mask, pg, s.refined); break;
+        default: secondary_kernel<0><<<grid, block, 0, st>>>(g, s.gray, s.wta4, s.edge2, s.agg_vol, s.gather_mask, pg, s.refined); break;
     }
     return cudaGetLastError();
 }

@@ -145,13 +145,13 @@ def test_screened_matches_reference_fixtures(name):
     """Screened CUDA path vs the reference's own kernel outputs (untainted cells)."""
     g = load_golden(name)
     kw = {f: int(v) for f, v in zip(O.CONFIG_FIELDS, g["config"])}
-    if kw["min_disparity"] // kw["downscale_factor"]:
-        pytest.skip("reference-compat mode materialises the volume: the screen is off there")
     L = g["agg"].shape[2]
     if not 3 <= L <= 128 or kw["ncc_patch_radius"] != 1:
         pytest.skip("screen unsupported for this configuration")
     cfg = oracle_config_from_array(O, g["config"])
-    t = O.run(cfg, g["left"], g["right"], mode=O.MODE_SAFE, want=("taint_agg", "taint_refined", "taint_out"))
+    # (min_disparity != 0, g5_k2_mind: reference-compat mode behind the screen = the gather pass)
+    mode = O.MODE_COMPAT if kw["min_disparity"] // kw["downscale_factor"] else O.MODE_SAFE
+    t = O.run(cfg, g["left"], g["right"], mode=mode, want=("taint_agg", "taint_refined", "taint_out"))
     info = {}
     got = run_cuda_all_stages(g["left"], g["right"], kw, variant="fast", dtype="f32", volumes=False, screen=True, info=info)
     assert info["screen_active"]
@@ -499,6 +499,55 @@ def test_min_disparity_compat_switch(variant):
         assert mismatch(on[st], ref_on[st]) == 0, st
         assert mismatch(off[st], ref_off[st]) == 0, st
     assert mismatch(ref_on["refined"], ref_off["refined"]) > 0   # the bug is observable on this input
+
+
+GATHER_SHAPES = [
+    # (H, W, K, min_d, max_d): reference-compat mode BEHIND THE SCREEN (gather pass, Geom::abs_index == 2)
+    (64, 128, 2, 8, 39),       # the g5 fixture's configuration: d* + min_ds + 1 > L happens -> previous pixel's levels
+    (150, 560, 2, 75, 262),    # the reference's default disparity range, several tiles, first-column / row-wrap sources
+    (96, 400, 2, 80, 99),      # min_ds = 40 > L = 10: negative pad_index reaches four pixels back
+    (70, 300, 1, 17, 80),      # K = 1
+    (120, 420, 3, 30, 150),    # K = 3
+    (80, 260, 2, 6, 133),      # L = 64, small min_ds: mostly same-pixel reads at other levels
+]
+
+
+@pytest.mark.parametrize("shape", GATHER_SHAPES)
+@pytest.mark.parametrize("dtype", ["u8", "f32"])
+def test_min_disparity_behind_the_screen_gather_pass(shape, dtype):
+    """min_disparity/K != 0 with the level screen ON: WTA from the screened kernel, then the gather pass evaluates exactly
+    the level pairs the reference's absolute-index reads touch (compact per-tile volume).  Must equal the oracle's
+    MODE_COMPAT on every cell, the whole-volume path (screen off) and, with compat off, MODE_SAFE."""
+    import torch
+    from stereo_depth_b200 import cuda_depth
+    H, W, K, mn, mx = shape
+    kw = cfg_kw(H, W, K, mn, mx)
+    l, r, _ = make_pair(H, W, mx + 1, seed=600 + H)
+    ref = oracle_all(kw, l, r, O.MODE_COMPAT)
+    info = {}
+    on = run_cuda_all_stages(l, r, kw, variant="fast", dtype=dtype, volumes=False, screen=True, info=info)
+    assert info["screen_active"] and 0.0 < info["evaluated_fraction"] <= 1.0
+    off = run_cuda_all_stages(l, r, kw, variant="fast", dtype=dtype, volumes=False, screen=False)
+    for st in ("wta", "agg3", "refined", "out"):
+        assert mismatch(on[st], ref[st]) == 0, (st, "gather")
+        assert mismatch(off[st], ref[st]) == 0, (st, "whole volume")
+    safe = run_cuda_all_stages(l, r, kw, variant="fast", dtype=dtype, volumes=False, screen=True, compat=False)
+    ref_safe = oracle_all(kw, l, r, O.MODE_SAFE)
+    for st in ("wta", "refined", "out"):
+        assert mismatch(safe[st], ref_safe[st]) == 0, (st, "compat off")
+    # launches: gray+pool, pad, screen, WTA, targets, gather, secondary, fill
+    sm = cuda_depth.StereoMatching(cuda_depth.StereoMatchingConfiguration(**kw), frames_per_launch=1)
+    sm.set_variant("fast")
+    assert sm.launches_per_call(1) == 8
+    # a batch with chunks, the range flag raised by out-of-range floats in one chunk (the gather masks must still hold)
+    lt, rt = torch.from_numpy(l).float().cuda(), torch.from_numpy(r).float().cuda()
+    wild = lt.clone()
+    wild[:, :8, :8] = 900.0
+    bl, br = torch.stack([lt, wild, lt]), torch.stack([rt, rt, rt])
+    got = sm.compute_disparity_batch(bl, br).cpu().numpy()
+    assert mismatch(got[0], ref["out"]) == 0 and mismatch(got[2], ref["out"]) == 0
+    ref_wild = O.run(O.make_config(**kw), wild.cpu().numpy(), r, mode=O.MODE_COMPAT, want=("out",))["out"]
+    assert mismatch(got[1], ref_wild) == 0
 
 
 def test_consumers_metrics_and_point_cloud():

@@ -84,7 +84,7 @@ def test_property_every_schedule_equals_the_oracle(c):
     if variant == "ws" and L > 150:
         variant = "fast"
     if variant == "screened":
-        variant, screen = "fast", (3 <= L <= 128 and mn // K == 0) or None
+        variant, screen = "fast", (3 <= L <= 128) or None   # (min_disparity/K != 0 behind the screen: gather pass)
     mode = O.MODE_COMPAT if mn // K else O.MODE_SAFE
     ref = O.run(O.make_config(**kw), left, right, mode=mode, want=("wta", "refined", "out"))
     got = _run(kw, left, right, variant, screen)

@@ -17,7 +17,12 @@ variants = [a for a in sys.argv[1:] if a in ("generic", "fast", "ws")] or ["fast
 nf = int(os.environ.get("NF", "8"))
 for name in names:
     H, W, K, D = cases[name]
-    l, r = make_batch(2, H, W, D)
+    if name == "REFDEFAULT":
+        # scene disparities must lie inside [75, 262]: a D=128 scene (8..96) with the right view shifted by another 75 columns
+        l, r = make_batch(2, H, W, 128)
+        r = np.roll(r, -75, axis=3)
+    else:
+        l, r = make_batch(2, H, W, D)
     l = torch.from_numpy(np.concatenate([l] * (nf // 2))).cuda()
     r = torch.from_numpy(np.concatenate([r] * (nf // 2))).cuda()
     for variant in variants:
