@@ -169,6 +169,13 @@ int sd_launches_per_call(sd_handle *h, int n_frames);
 
 int sd_frames_per_launch(sd_handle *h);
 
+/* Level split for launches that cannot fill the GPU (one small frame, a thin row band): the unscreened specialised
+ * kernel then spreads every tile's disparity levels over several blocks and a small kernel merges the partial
+ * winner-take-all records (identical results: the maximum is taken in ascending level order with strict '>').
+ * sd_level_split: the split a launch of n_frames frames would use (1 = none); sd_set_level_split(h, 0) disables it. */
+int sd_set_level_split(sd_handle *h, int on);
+int sd_level_split(sd_handle *h, int n_frames);
+
 /* The fused-kernel variant the next sd_compute will run: 1 generic, 2 specialised, 3 warp-specialised
  * (variant 0 = auto picks 2 or 3 per shape from a wave/tile cost model, see sd_create in api.cu). */
 int sd_active_variant(sd_handle *h);

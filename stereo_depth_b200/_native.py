@@ -19,7 +19,7 @@ CONFIG_FIELDS = ("height", "width", "downscale_factor", "min_disparity", "max_di
 # every symbol include/stereo_b200.h declares
 EXPORTS = ("sd_abi_version", "sd_config_default", "sd_dims", "sd_create", "sd_destroy", "sd_compute",
            "sd_compute_range", "sd_set_band", "sd_band_p2p_init", "sd_band_p2p_connect", "sd_band_p2p_compute", "sd_compute_host", "sd_get_stage", "sd_set_debug_volumes", "sd_set_compat", "sd_set_variant",
-           "sd_launches_per_call", "sd_frames_per_launch", "sd_active_variant", "sd_set_screen", "sd_screen_active", "sd_screen_stats", "sd_screen_paused", "sd_profile_enable", "sd_profile_read", "sd_profile_read_detail", "sd_metrics", "sd_point_cloud", "sd_check_guards", "sd_stage_pointer",
+           "sd_launches_per_call", "sd_frames_per_launch", "sd_active_variant", "sd_set_screen", "sd_screen_active", "sd_screen_stats", "sd_screen_paused", "sd_profile_enable", "sd_profile_read", "sd_profile_read_detail", "sd_metrics", "sd_point_cloud", "sd_check_guards", "sd_stage_pointer", "sd_set_level_split", "sd_level_split",
            "sd_last_error", "sd_last_cuda_error")
 
 
@@ -77,6 +77,8 @@ def lib():
     L.sd_profile_read_detail.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.sd_metrics.argtypes = [vp, vp, C.c_longlong, C.c_float, C.c_float, vp, vp]
     L.sd_point_cloud.argtypes = [vp, ip, ip, C.c_float, C.c_float, vp, vp, vp]
+    L.sd_set_level_split.argtypes = [vp, ip]
+    L.sd_level_split.argtypes = [vp, ip]
     L.sd_stage_pointer.argtypes = [vp, ip, ip, C.POINTER(vp)]
     L.sd_check_guards.argtypes = [vp, C.POINTER(C.c_longlong)]
     L.sd_last_error.argtypes = [vp]
@@ -192,6 +194,17 @@ class Handle:
         self.check(lib().sd_profile_read_detail(self._h, ms, n))
         names = ("gray_pool", "pad_planes", "level_screen", "cost_agg_wta", "secondary", "fill")
         return {k: (ms[i], n[i]) for i, k in enumerate(names)}
+
+    def set_level_split(self, on):
+        self.check(lib().sd_set_level_split(self._h, 1 if on else 0))
+
+    def level_split_for(self, n_frames=1):
+        return lib().sd_level_split(self._h, n_frames)
+
+    @property
+    def level_split(self):
+        """Level split of a one-frame launch (1 = none)."""
+        return lib().sd_level_split(self._h, 1)
 
     @property
     def frames_per_launch(self):

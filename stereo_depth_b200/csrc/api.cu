@@ -33,6 +33,8 @@ struct sd_handle {
     int sms, per_sm_fast;  // SM count and resident blocks per SM of the specialised kernel (launch cost models)
     bool screen;     // certified level screen in front of the specialised kernel (default on where supported)
     int epoch;       // chunk counter, tags the out-of-range flag of the screen
+    size_t parts_capacity;  // pixels the part slots of a level-split launch can hold (Scratch::wta4_parts)
+    bool split_off;  // sd_set_level_split(h, 0): never split (tuning / tests)
     int abs_mode;    // layout of Scratch::agg_vol for the chunk in flight: 0 none, 1 whole volume, 2 compact (gather pass)
     // Adaptive policy: the screen only pays off when it removes work.  The last block of every screen launch posts
     // {chunk tag, pairs screened, pairs flagged} as one 64-bit store to mapped host memory (no copy, no wait); the
@@ -217,12 +219,53 @@ bool screen_pays(const sd_handle *h, int frames) {
 
 bool screen_active(const sd_handle *h, int frames) { return screen_allowed(h) && screen_pays(h, frames); }
 
+// LEVEL SPLIT of the unscreened specialised kernel for launches that do not fill the GPU (single frames, thin row
+// bands): a tile's L/2 level pairs go to `split` blocks, so a launch of T tiles has T*split blocks of L/(2 split)
+// passes each instead of T blocks of L/2.  Cost model in pass-times of one block: rounds * (passes + ~1.5 for staging
+// the bands and the part records).  Returns the best split (1 = off) and its cost.
+constexpr int kMaxSplit = 16;
+constexpr double kSplitOverhead = 1.5;
+int plan_split(const sd_handle *h, int frames, bool need_buffers, double *cost_out) {
+    const Geom &g = h->g;
+    const int M = ((g.L + 1) & ~1) / 2;
+    const long long tiles = (long long)((g.Wd + kTileW - 1) / kTileW) * ((g.Hd + kTileH - 1) / kTileH) * frames;
+    const long long slots = (long long)h->sms * h->per_sm_fast;
+    auto cost = [&](int S) { return (double)((tiles * S + slots - 1) / slots) * ((M + S - 1) / S + kSplitOverhead); };
+    int best = 1;
+    double best_cost = cost(1);
+    const bool can = mbm_wta_fast_supported(g) && !h->dbg_cost && !h->dbg_agg && !h->s.agg_vol && (!need_buffers || h->s.wta4_parts);
+    for (int S = 2; can && S <= kMaxSplit && S <= M; S++) {
+        if (need_buffers && (size_t)S * frames * g.Hd * g.Wd > h->parts_capacity) break;
+        if (cost(S) < 0.9 * best_cost && cost(S) < 0.9 * cost(1)) {
+            best = S;
+            best_cost = cost(S);
+        }
+    }
+    if (cost_out) *cost_out = best_cost;
+    return best;
+}
+
 // 1 generic, 2 specialised, 3 warp-specialised -- for a launch of `frames` frames
 int active_variant(const sd_handle *h, int frames) {
     const bool fast = h->s.padl && ((h->variant >= 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g)));
-    const bool ws = (h->variant == 3 || (h->variant == 0 && h->auto_ws && !screen_active(h, frames))) && h->s.padl &&
-                    !h->dbg_cost && !h->dbg_agg && mbm_wta_ws_supported(h->g);
+    bool ws = (h->variant == 3 || (h->variant == 0 && h->auto_ws && !screen_active(h, frames))) && h->s.padl &&
+              !h->dbg_cost && !h->dbg_agg && mbm_wta_ws_supported(h->g);
+    if (ws && h->variant == 0) {
+        // the warp-specialised schedule (64x64 tiles, one block per SM, ~0.96 of the two-phase pass time) has no level
+        // split: for small launches the split two-phase kernel can be the faster one
+        const Geom &g = h->g;
+        const long long tiles_ws = (long long)((g.Wd + kTileW - 1) / kTileW) * ((g.Hd + 63) / 64) * frames;
+        const double cost_ws = (double)((tiles_ws + h->sms - 1) / h->sms) * (((g.L + 1) & ~1) / 2 + kSplitOverhead) * 0.96;
+        double cost_split = 0.0;
+        if (plan_split(h, frames, true, &cost_split) > 1 && cost_split < 0.9 * cost_ws) ws = false;
+    }
     return ws ? 3 : (fast ? 2 : 1);
+}
+
+// level split of the next launch of `frames` frames (1 = off): only for the unscreened specialised kernel
+int active_split(const sd_handle *h, int frames) {
+    if (h->split_off || active_variant(h, frames) != 2 || screen_active(h, frames)) return 1;
+    return plan_split(h, frames, true, nullptr);
 }
 
 int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int frames, float *out, cudaStream_t st,
@@ -265,7 +308,10 @@ int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int 
             SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, wta_only, nullptr, nullptr, st, true));
             SD_CUDA(h, launch_abs_targets(h->g, frames, h->s, st));
             SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, nullptr, nullptr, st, false, true));
-        } else if (v == 2) SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st, screen));
+        } else if (v == 2) {
+            const int split = screen ? 1 : active_split(h, frames);
+            SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st, screen, false, split));
+        }
         else SD_CUDA(h, launch_mbm_wta_generic(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
     }
     if (full && (rc = prof_mark(h, st)) != SD_OK) return rc;
@@ -432,6 +478,18 @@ int sd_create(const sd_config *cfg, int device, int frames_per_launch, sd_handle
         SD_CUDA(h, scratch_alloc(h, (void **)&h->s.padr, F * (size_t)pg.rows * pg.pwr * sizeof(float)));
         SD_CUDA(h, scratch_alloc(h, (void **)&h->s.range_flag, sizeof(int)));
         SD_CUDA(h, cudaMemset(h->s.range_flag, 0, sizeof(int)));
+        {   // part slots for level-split launches: sized for the largest split any launch size of this handle would pick
+            size_t need = 0;
+            for (int f = 1; f <= h->chunk; f++) {
+                const int S = plan_split(h, f, false, nullptr);
+                if (S > 1 && (size_t)S * f * nd > need) need = (size_t)S * f * nd;
+            }
+            if (need > 0 && need * (sizeof(float4) + sizeof(float2)) <= ((size_t)1 << 30)) {
+                SD_CUDA(h, scratch_alloc(h, (void **)&h->s.wta4_parts, need * sizeof(float4)));
+                SD_CUDA(h, scratch_alloc(h, (void **)&h->s.edge2_parts, need * sizeof(float2)));
+                h->parts_capacity = need;
+            }
+        }
         if (mbm_screen_supported(g)) {
             SD_CUDA(h, scratch_alloc(h, (void **)&h->s.pass_mask, F * (size_t)pg.tiles_x * pg.tiles_y * 4 * sizeof(unsigned)));
             SD_CUDA(h, scratch_alloc(h, (void **)&h->s.gather_mask, F * (size_t)pg.tiles_x * pg.tiles_y * 4 * sizeof(unsigned)));
@@ -478,6 +536,8 @@ int sd_destroy(sd_handle *h) {
         scratch_free(h, h->s.wta4);
         scratch_free(h, h->s.edge2);
         scratch_free(h, h->s.refined);
+        scratch_free(h, h->s.wta4_parts);
+        scratch_free(h, h->s.edge2_parts);
         if (h->ev_last) cudaEventDestroy(h->ev_last);
         scratch_free(h, h->s.agg_vol);
         scratch_free(h, h->s.padl);
@@ -843,12 +903,24 @@ int sd_launches_per_call(sd_handle *h, int n_frames) {
         const int nf = base + (c < extra ? 1 : 0);
         const bool scr = active_variant(h, nf) == 2 && screen_active(h, nf);
         // (+2 behind the screen in reference-compat mode: absolute-index targets + gather pass)
-        total += 4 + (active_variant(h, nf) >= 2 ? 1 : 0) + (scr ? 1 : 0) + (scr && h->s.agg_vol ? 2 : 0);
+        total += 4 + (active_variant(h, nf) >= 2 ? 1 : 0) + (scr ? 1 : 0) + (scr && h->s.agg_vol ? 2 : 0) +
+                 (active_split(h, nf) > 1 ? 1 : 0);   // + merge of the part slots
     }
     return total;
 }
 
 int sd_frames_per_launch(sd_handle *h) { return h ? h->chunk : 0; }
+
+int sd_set_level_split(sd_handle *h, int on) {
+    if (!h) return SD_ERR_BAD_ARG;
+    h->split_off = (on == 0);
+    return SD_OK;
+}
+
+int sd_level_split(sd_handle *h, int n_frames) {
+    if (!h || n_frames <= 0) return 0;
+    return active_split(h, n_frames > h->chunk ? h->chunk : n_frames);
+}
 
 int sd_active_variant(sd_handle *h) { return h ? active_variant(h, h->chunk) : 0; }
 

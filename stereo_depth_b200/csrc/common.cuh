@@ -92,6 +92,8 @@ struct Scratch {
     float4 *wta4;
     float2 *edge2;
     float *refined;
+    float4 *wta4_parts;   // [split][frames][Hd*Wd] part slots of a level-split launch (small launches only), else NULL
+    float2 *edge2_parts;  // [split][frames][Hd*Wd]
     float *agg_vol;  // [F][L][Hd*Wd] (plane-major) aggregated volume, only in reference-compat mode (abs_index), else NULL
     float *padl, *padr;  // [F][rows][pwl], [F][rows][pwr] wrap-padded pooled planes (PadGeom), NULL if unsupported
     // Certified level screen (mbm_screen.cu), all NULL when unsupported:
@@ -126,8 +128,10 @@ bool mbm_wta_fast_supported(const Geom &g);
 // use_screen: run only the level pairs flagged in s.pass_mask (written by launch_mbm_screen for the same chunk)
 // gather: no WTA; evaluate the level pairs flagged in s.gather_mask and store their aggregated values into s.agg_vol
 // in the compact per-tile layout (Geom::abs_index == 2)
+// split > 1 (unscreened, no volumes): every tile's level pairs are spread over `split` blocks (part slots in
+// s.wta4_parts / s.edge2_parts), then merged into s.wta4 / s.edge2 -- for launches too small to fill the GPU otherwise
 cudaError_t launch_mbm_wta_fast(const Geom &g, int frames, const Scratch &s, float *dbg_cost,
-                                float *dbg_agg, cudaStream_t st, bool use_screen = false, bool gather = false);
+                                float *dbg_agg, cudaStream_t st, bool use_screen = false, bool gather = false, int split = 1);
 // marks in s.gather_mask (zeroed by the caller) the level pairs the absolute-index reads of secondary matching need
 cudaError_t launch_abs_targets(const Geom &g, int frames, const Scratch &s, cudaStream_t st);
 // floats per frame of the compact layout (>= Hd*Wd*L)

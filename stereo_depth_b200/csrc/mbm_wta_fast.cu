@@ -59,7 +59,7 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
                     float4 *__restrict__ wta4, float2 *__restrict__ edge2, float *__restrict__ dbg_cost,
                     float *__restrict__ dbg_agg, float *__restrict__ agg_planes, const unsigned *__restrict__ pass_mask,
                     const int *__restrict__ range_flag, int range_epoch, const int *__restrict__ tile_order,
-                    const int *__restrict__ bucket_count) {
+                    const int *__restrict__ bucket_count, int n_split) {
     using C = Cfg<BH>;
     extern __shared__ float4 smem4[];
     float4 *plane = smem4;                                              // [PRW][42] chunks of (cell,level) pairs
@@ -89,9 +89,14 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
         if (found) tile = tile_order[slot];
     }
     const int tile_x = tile % gridDim.x, tile_y = (tile / gridDim.x) % gridDim.y;
-    const int frame = tile / (gridDim.x * gridDim.y), r0 = tile_y * BH, c0 = tile_x * BW;
+    // LEVEL SPLIT (small launches: single frames, thin row bands): gridDim.z = frames * n_split, and this block evaluates
+    // only the level pairs [m_begin, m_end) of its tile into the part-th slot of the part arrays (wta4 / edge2 then point
+    // at [n_split][frames][Hd*Wd]); merge_parts_kernel combines the slots.  n_split == 1: the whole range, final arrays.
+    const int zf = tile / (gridDim.x * gridDim.y);
+    const int frame = zf / n_split, part = zf - frame * n_split, r0 = tile_y * BH, c0 = tile_x * BW;
     const int Hd = g.Hd, Wd = g.Wd, L = g.L;
     const int Lp = (L + 1) & ~1, M = Lp >> 1;
+    const int m_begin = (part * M) / n_split, m_end = ((part + 1) * M) / n_split;
     const size_t np = (size_t)Hd * Wd;
     const int RW = pg.rw;
 
@@ -128,7 +133,7 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
     // pixel -- which keeps ~50 registers free for the adder chains.  Pixels outside the image start at
     // +inf and therefore never store.
     const int px0 = r0 + 4 * ty, py0 = c0 + 4 * tx;  // first owned pixel
-    const size_t o00 = (size_t)frame * np + (size_t)px0 * Wd + py0;
+    const size_t o00 = ((size_t)part * (gridDim.z / n_split) + frame) * np + (size_t)px0 * Wd + py0;
     float best[16], prev[16];
     unsigned pend = 0;  // bit k: record k still waits for A[d*+1] (arrives with the next pass)
 #pragma unroll
@@ -148,7 +153,7 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
             if (++spins > (1 << 24)) __trap();  // a lost transaction must not hang the GPU
     }
 
-    for (int m = 0; m < M; m++) {
+    for (int m = m_begin; m < m_end; m++) {
         // Skipped level pairs leave prev[] / pend stale.  That only ever reaches records that a later level
         // overwrites: the reference's arg-max d* is always evaluated together with d*-1 and d*+1 (circular).
         if (!((s_pass[(m >> 5) & 3] >> (m & 31)) & 1u)) continue;
@@ -422,14 +427,15 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
                 }
             }
         }
-        if (m == 0) {
+        if (m == m_begin) {
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 const int x = px0 + (k >> 2), y = py0 + (k & 3);
                 if (x < Hd && y < Wd) {
                     const size_t o = o00 + (size_t)(k >> 2) * Wd + (k & 3);
-                    edge2[o].x = hv[k].x;                                    // A[0]
-                    wta4[o] = make_float4(0.0f, 0.0f, hv[k].x, hv[k].y);      // record if nothing ever beats FLT_MIN
+                    edge2[o].x = hv[k].x;                                    // A[0] (first level of this part)
+                    // record if nothing ever beats FLT_MIN; in a part slot d = -1 says "no maximum in this range"
+                    wta4[o] = make_float4(n_split > 1 ? -1.0f : 0.0f, 0.0f, hv[k].x, hv[k].y);
                 }
             }
         }
@@ -460,13 +466,42 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         const int x = px0 + (k >> 2), y = py0 + (k & 3);
-        if (x < Hd && y < Wd) edge2[o00 + (size_t)(k >> 2) * Wd + (k & 3)].y = prev[k];  // A[L-1]
+        if (x < Hd && y < Wd) edge2[o00 + (size_t)(k >> 2) * Wd + (k & 3)].y = prev[k];  // A[L-1] (last level of this part)
     }
+}
+
+// Combines the part slots of a level-split launch into the final records: the maximum over the parts in ascending level
+// order with strict '>' (the first maximum wins, wta_disparity_selection.cu:22-29), its neighbours A[d*-1] / A[d*+1] taken
+// from the adjacent part's edge values when d* sits on a part boundary, and (A[0], A[L-1]) from the outermost parts.
+__global__ void merge_parts_kernel(const float4 *__restrict__ pw, const float2 *__restrict__ pe, float4 *__restrict__ wta4,
+                                   float2 *__restrict__ edge2, size_t n, int S, int M) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float best = kFltMin;
+    float4 out = pw[i];
+    int wp = -1;
+    for (int p = 0; p < S; p++) {
+        const float4 r = pw[(size_t)p * n + i];
+        if (r.x >= 0.0f && r.z > best) {
+            best = r.z;
+            out = r;
+            wp = p;
+        }
+    }
+    if (wp < 0) {
+        out = make_float4(0.0f, 0.0f, out.z, out.w);   // nothing beats FLT_MIN: level 0, (A[0], A[1]) like the unsplit kernel
+    } else {
+        const int d = (int)out.x, l0 = 2 * ((wp * M) / S), l1 = 2 * (((wp + 1) * M) / S) - 1;
+        if (d == l0 && wp > 0) out.y = pe[(size_t)(wp - 1) * n + i].y;
+        if (d == l1 && wp < S - 1) out.w = pe[(size_t)(wp + 1) * n + i].x;
+    }
+    wta4[i] = out;
+    edge2[i] = make_float2(pe[i].x, pe[(size_t)(S - 1) * n + i].y);
 }
 
 template <int BH, bool DBG, int MODE, int STORE>
 cudaError_t launch_t(const Geom &g, int frames, const Scratch &s, float *dbg_cost, float *dbg_agg, cudaStream_t st,
-                     bool use_screen = false) {
+                     bool use_screen = false, int split = 1) {
     const size_t smem = smem_bytes<BH>(g.L, g.min_ds);
     const PadGeom pg = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
     // per-device attribute: set on every launch (cheap) so multi-GPU processes stay correct
@@ -476,12 +511,26 @@ cudaError_t launch_t(const Geom &g, int frames, const Scratch &s, float *dbg_cos
     if (STORE == 2) {
         mbm_wta_fast_kernel<BH, DBG, MODE, STORE><<<grid, Cfg<BH>::NT, smem, st>>>(
             g, pg, s.padl, s.padr, s.wta4, s.edge2, nullptr, nullptr, s.agg_vol, s.gather_mask, s.range_flag, s.range_epoch,
-            nullptr, s.bucket_count);
+            nullptr, s.bucket_count, 1);
+        return cudaGetLastError();
+    }
+    if (split > 1) {
+        // level split: every tile's level pairs are spread over `split` blocks writing part slots, then merged
+        if (use_screen || STORE != 0 || DBG || !s.wta4_parts || !s.edge2_parts) return cudaErrorNotSupported;
+        grid.z = frames * split;
+        mbm_wta_fast_kernel<BH, DBG, MODE, STORE><<<grid, Cfg<BH>::NT, smem, st>>>(
+            g, pg, s.padl, s.padr, s.wta4_parts, s.edge2_parts, nullptr, nullptr, nullptr, nullptr, s.range_flag, s.range_epoch,
+            nullptr, s.bucket_count, split);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        const size_t n = (size_t)frames * g.Hd * g.Wd;
+        merge_parts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s.wta4_parts, s.edge2_parts, s.wta4, s.edge2, n, split,
+                                                                      ((g.L + 1) & ~1) / 2);
         return cudaGetLastError();
     }
     mbm_wta_fast_kernel<BH, DBG, MODE, STORE><<<grid, Cfg<BH>::NT, smem, st>>>(
         g, pg, s.padl, s.padr, s.wta4, s.edge2, dbg_cost, dbg_agg, s.agg_vol, use_screen ? s.pass_mask : nullptr,
-        s.range_flag, s.range_epoch, use_screen ? s.tile_order : nullptr, s.bucket_count);
+        s.range_flag, s.range_epoch, use_screen ? s.tile_order : nullptr, s.bucket_count, 1);
     return cudaGetLastError();
 }
 
@@ -506,7 +555,7 @@ bool mbm_wta_fast_supported(const Geom &g) {
 // The wrap-padded planes (launch_pad_pooled) and, with use_screen, the pass masks of this chunk (launch_mbm_screen)
 // must already be in flight on `st`.
 cudaError_t launch_mbm_wta_fast(const Geom &g, int frames, const Scratch &s, float *dbg_cost, float *dbg_agg,
-                                cudaStream_t st, bool use_screen, bool gather) {
+                                cudaStream_t st, bool use_screen, bool gather, int split) {
     if (!mbm_wta_fast_supported(g) || !s.padl || !s.padr) return cudaErrorNotSupported;
     if (gather) {
         if (!s.agg_vol || !s.gather_mask) return cudaErrorNotSupported;
@@ -516,9 +565,9 @@ cudaError_t launch_mbm_wta_fast(const Geom &g, int frames, const Scratch &s, flo
     if (dbg_cost || dbg_agg) return launch_t<32, true, 0, 1>(g, frames, s, dbg_cost, dbg_agg, st);
     if (s.agg_vol) return launch_t<32, false, 2, 1>(g, frames, s, nullptr, nullptr, st);
     switch (fast_mode()) {
-        case 1: return launch_t<32, false, 1, 0>(g, frames, s, nullptr, nullptr, st, use_screen);
-        case 2: return launch_t<32, false, 2, 0>(g, frames, s, nullptr, nullptr, st, use_screen);
-        default: return launch_t<32, false, 0, 0>(g, frames, s, nullptr, nullptr, st, use_screen);
+        case 1: return launch_t<32, false, 1, 0>(g, frames, s, nullptr, nullptr, st, use_screen, split);
+        case 2: return launch_t<32, false, 2, 0>(g, frames, s, nullptr, nullptr, st, use_screen, split);
+        default: return launch_t<32, false, 0, 0>(g, frames, s, nullptr, nullptr, st, use_screen, split);
     }
 }
 

@@ -166,6 +166,13 @@ class StereoMatching:
     def set_variant(self, v):
         self._handle.set_variant({"auto": 0, "generic": 1, "fast": 2, "ws": 3}.get(v, v))
 
+    def set_level_split(self, on=True):
+        """Level split of launches too small to fill the GPU (default on; results identical)."""
+        self._handle.set_level_split(on)
+
+    def level_split(self, n_frames=1):
+        return self._handle.level_split_for(n_frames)
+
     def set_screen(self, on=True):
         """Certified level screen in front of the fused kernel (default on where supported; results identical)."""
         self._handle.set_screen(on)

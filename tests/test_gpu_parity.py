@@ -360,7 +360,12 @@ def test_batches_chunks_and_host_path_agree():
     # 6 kernels per chunk (gray+pool, plane padding, level screen, cost+agg+WTA, secondary, fill), 3 chunks
     assert be.native.screen_active and be.native.launches_per_call(n) == 6 * 3
     be.native.set_screen(False)
-    assert be.native.launches_per_call(n) == 5 * 3
+    # unscreened launches this small split every tile's levels over several blocks: + 1 merge kernel per chunk
+    assert be.native.level_split(3) > 1 and be.native.launches_per_call(n) == 6 * 3
+    be.native.set_level_split(False)
+    assert be.native.level_split(3) == 1 and be.native.launches_per_call(n) == 5 * 3
+    assert mismatch(be.process_batch(torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()).cpu().numpy(), singles) == 0
+    be.native.set_level_split(True)
     assert mismatch(be.process_batch(torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()).cpu().numpy(), singles) == 0
 
 
@@ -548,6 +553,50 @@ def test_min_disparity_behind_the_screen_gather_pass(shape, dtype):
     assert mismatch(got[0], ref["out"]) == 0 and mismatch(got[2], ref["out"]) == 0
     ref_wild = O.run(O.make_config(**kw), wild.cpu().numpy(), r, mode=O.MODE_COMPAT, want=("out",))["out"]
     assert mismatch(got[1], ref_wild) == 0
+
+
+SPLIT_SHAPES = [
+    # (H, W, K, min_d, max_d): launches of one frame that cannot fill the GPU -> level split of the unscreened kernel
+    (96, 160, 2, 0, 31), (75, 133, 2, 0, 30), (130, 150, 2, 0, 2), (66, 70, 2, 0, 0), (136, 264, 2, 0, 63),
+    (72, 600, 2, 0, 511), (60, 520, 1, 0, 129), (318, 3840, 2, 0, 255),   # the last: a C4 row band on 8 GPUs
+]
+
+
+@pytest.mark.parametrize("shape", SPLIT_SHAPES)
+def test_level_split_equals_unsplit(shape):
+    """Every tile's level pairs spread over `split` blocks + merge_parts_kernel == the unsplit kernel == the oracle,
+    including the FLT_MIN rule (nothing beats the initial best: level 0) and odd level counts."""
+    import torch
+    from stereo_depth_b200 import cuda_depth
+    H, W, K, mn, mx = shape
+    kw = cfg_kw(H, W, K, mn, mx)
+    l, r, _ = make_pair(H, W, mx + 1, seed=700 + H)
+    ref = O.run(O.make_config(**kw), l, r, want=("wta", "agg", "refined", "out"))
+    ref["agg3"] = agg3_from_volume(ref["agg"], ref["wta"], 0)
+    L = mx // K + 1
+    sm = cuda_depth.StereoMatching(cuda_depth.StereoMatchingConfiguration(**kw), frames_per_launch=1)
+    sm.set_variant("fast")
+    sm.set_screen(False) if 3 <= L <= 128 else None
+    lt, rt = torch.from_numpy(l).cuda(), torch.from_numpy(r).cuda()
+    outs = {}
+    for split in (True, False):
+        sm.set_level_split(split)
+        assert (sm.level_split(1) > 1) == (split and L >= 4), (split, sm.level_split(1))
+        out = sm.compute_disparity_map(lt, rt).cpu().numpy().copy()
+        outs[split] = {st: sm.stage(st).cpu().numpy() for st in ("wta", "agg3", "refined")}
+        outs[split]["out"] = out
+        for st in ("wta", "agg3", "refined", "out"):
+            assert mismatch(outs[split][st], ref[st]) == 0, (st, split, sm.level_split(1))
+    # out-of-range floats: every aggregated cost is negative, nothing beats FLT_MIN -> level 0 in every part
+    sm.set_level_split(True)
+    rng = np.random.default_rng(5)
+    lf = (rng.random((3, H, W)) * 4000).astype(np.float32)
+    rf = (rng.random((3, H, W)) * 4000 + 5000).astype(np.float32)
+    refw = O.run(O.make_config(**kw), lf, rf, want=("wta", "refined", "out"))
+    out = sm.compute_disparity_map(torch.from_numpy(lf).cuda(), torch.from_numpy(rf).cuda()).cpu().numpy()
+    assert np.all(refw["wta"] == 0)
+    assert mismatch(sm.stage("wta").cpu().numpy(), refw["wta"]) == 0 and mismatch(out, refw["out"]) == 0
+    assert mismatch(sm.stage("refined").cpu().numpy(), refw["refined"]) == 0
 
 
 def test_consumers_metrics_and_point_cloud():

@@ -55,7 +55,8 @@ def three_way(left, right, H, W, K, mn, mx, min_clean, variants=("auto", "fast")
     stages, ref_cuda_depth, run_reference = ref_modules()
     kw = dict(height=H, width=W, downscale_factor=K, min_disparity=mn, max_disparity=mx)
     torch.cuda.empty_cache()
-    ref = run_reference(stages, ref_cuda_depth, left, right, H, W, K, mn, mx, keep_volumes=False)
+    ref = run_reference(stages, ref_cuda_depth, left, right, H, W, K, mn, mx, keep_volumes=False, api_needs_large_pool=True)
+    assert ref["out_api"] is not None, "test images must have gray planes >= 1 MiB (see run_reference)"
     torch.cuda.empty_cache()
     cfg = O.make_config(**kw)
     want = ("gray_l", "gray_r", "pool_l", "pool_r", "wta", "refined", "out", "taint_agg", "taint_refined", "taint_out")
@@ -131,10 +132,11 @@ def test_live_reference_natural_pair_from_zero():
 
 CROPS = [
     # (row0, col0, H, W, K, min_d, max_d)   crops of the natural pair: low texture, ties, K = 1, 2, 3, min_disparity != 0
-    (0, 0, 360, 640, 2, 0, 127),
+    # (every crop >= 262 400 pixels: the reference's buffers must come from the allocator's large pool, see run_reference)
+    (0, 0, 400, 704, 2, 0, 127),
     (700, 1200, 380, 720, 2, 0, 191),
-    (300, 600, 250, 499, 1, 0, 63),
-    (540, 100, 300, 801, 3, 30, 150),
+    (300, 600, 421, 641, 1, 0, 63),
+    (540, 100, 360, 801, 3, 30, 150),
 ]
 
 
