@@ -3,8 +3,9 @@
 // The fused kernel must evaluate every window sum as the reference's sequential fp32 chain (204 adds per
 // (pixel, level) cell) because the arg-max is sensitive to the summation order.  But only the levels that can
 // still BE the arg-max need that treatment.  This kernel computes every aggregated cost approximately -- the same
-// fp32 differences l-r as the reference, |l-r| summed separably (3-tap row sum -> 3x3 -> nested vertical 3/9/21-row
-// sums -> sliding horizontal 21/9/3-column sums; ~45 lane-ops per cell instead of 237) -- and keeps, per pixel, the set
+// fp32 differences l-r as the reference, |l-r| summed separably (per tap column: 3-row sum -> nested vertical 3/9/21-row
+// sums; then sliding horizontal 21/9/3-column sums with the 3x3 cost's horizontal 3-tap folded in; ~45 lane-ops per cell
+// instead of 237) -- and keeps, per pixel, the set
 // of levels whose approximate cost is within a RIGOROUS error bound of the pixel's approximate maximum.  The union over
 // a 32x64 tile of those levels and their two neighbours (the secondary matching reads A[d*-1], A[d*+1]; circular,
 // secondary_matching.cu:28-31), as level pairs, is the tile's pass mask: mbm_wta_fast_kernel then runs its exact
@@ -15,8 +16,9 @@
 //     a and sums |a| (dissimilarities); N*255 - sum|a| differs from the real sum of the reference's taps by at most
 //     N*255*u (u = 2^-24).  For pooled values in [0, 255] all terms are >= 0, so every fp32 summation order has a
 //     relative error below (#additions on the longest path) * u: the reference's chains stay within 89 u S_max of the
-//     real sum, the screen (12 nested adds, at most 35 sliding-window operations, one final subtraction) within
-//     50 u S_max, with S_max = 63*9*255 resp. 81*9*255: together below 1.5 in absolute terms; the analysis uses E = 4.
+//     real sum, the screen (10 nested vertical adds, at most 39 sliding-window operations + 2 for the 3-tap, one final
+//     subtraction) within 52 u S_max, with S_max = 63*9*255 resp. 81*9*255: together below 1.6 in absolute terms; the
+//     analysis uses E = 4.
 //   * A pixel whose approximate maximum A'max is >= T = 2^15 * 144600 * 185910 has all three sums of that level
 //     >= F = 2^15, hence A_ref[max] >= A'max (1 - 3.7e-4).  A level with A' < (1 - 2e-3) A'max has
 //     A_ref <= (H'+E)(V'+E)(C'+E)(1+2u) < A'max (1 - 3.7e-4)  (all sums >= F/2: factor (1 + E/(F/2))^3 = 1.00073;
@@ -31,9 +33,10 @@
 // Layout: one block of 128 threads per 32x64 tile (the fused kernel's tile), two blocks per SM (110 KB each: the
 // TMA-staged row bands + three row-sum buffers).  The block sees every level pair of its tile in ascending order, so
 // its running maxima settle early and the candidate bookkeeping goes quiet.  For L > 64 the right band is staged one
-// window of 32 level pairs at a time.  Phase A: thread = one of the 84 cost columns, walks the 54 band rows as a
-// software pipeline with all running sums in registers (all-positive nested sums: Y3 -> Z9 -> W21).  Phase B: thread =
-// (row, 16 columns): sliding sums along the row, similarities, product, candidate bookkeeping.  At the end thread 0
+// window of 32 level pairs at a time.  Phase A: thread = one of the 86 TAP columns (each |l-r| is formed exactly once),
+// walks the 54 band rows as a software pipeline with all running sums in registers (all-positive nested sums: 3-row sum
+// -> Y3 -> Z9 -> W21).  Phase B: thread = (row, 16 columns): sliding sums along the row with the cost's horizontal 3-tap
+// folded in (box filters commute), similarities, product, candidate bookkeeping.  At the end thread 0
 // writes the tile's mask, its cost class (heaviest-first schedule of the fused kernel) and the statistics that feed the
 // adaptive policy in api.cu.
 #include "common.cuh"
@@ -44,13 +47,14 @@ namespace {
 
 using namespace mbm;
 
-constexpr int SXW = 84;         // cost columns per tile (64 + 2*10)
+constexpr int SXW = 86;         // TAP columns per tile (64 + 2*10 cost columns + 1 tap column on either side)
 constexpr int SBR = 54;         // band rows used (32 + 2*10 + 2*1)
 // Row pitches of the three row-sum buffers in float2 cells.  Each is 16*odd bytes modulo 128, so the LDS.128 of eight
-// consecutive rows (phase B: lane = row) hit eight different 16-byte bank groups.  Y3 is kept for all 84 cost columns,
-// Z9 for columns 6..77 and W21 for columns 8..75 (all that phase B reads).
+// consecutive rows (phase B: lane = row) hit eight different 16-byte bank groups.  The buffers hold VERTICAL sums of
+// single tap columns (the horizontal 3-tap of the 3x3 cost is applied in phase B, where horizontal sums are cheap):
+// Y3 for all 86 tap columns, Z9 for tap columns 6..79 and W21 for tap columns 9..76 (all that phase B reads).
 constexpr int SPY = 86, SPZ = 74, SPW = 70;
-constexpr int SZ0 = 6, SZ1 = 78, SW0 = 8, SW1 = 76;
+constexpr int SZ0 = 6, SZ1 = 80, SW0 = 9, SW1 = 77;
 constexpr int SBUF = 32 * (SPY + SPZ + SPW);   // cells per group
 constexpr int SGT = 128;                       // threads per block
 constexpr float kKeep = 0.998f;             // candidate:  A' >= kKeep * running max        (eps  = 2e-3)
@@ -69,10 +73,13 @@ __host__ __device__ inline size_t screen_smem_bytes_windowed() {
 
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 
-// ---- phase A: cost column s of level pair (d0, d0+1); Y3 / Z9 / W21 = 3 / 9 / 21-row sums of the 3x3 cost ----------
-// Band row rr holds image row r0-11+rr; cost-plane row R = rr-2 (image row r0-10+R) is complete at step rr.
-// Left band column of (cost column s, dx) = s+5+dx; right band column of (s, dx, level d) = s+dx+Lp-d
-// (same indexing as the cost phase of mbm_wta_fast.cu).  Lane .x = level d0, .y = level d0+1.
+// ---- phase A: TAP column t of level pair (d0, d0+1); Y3 / Z9 / W21 = 3 / 9 / 21-row sums of the column's 3-row sums ----
+// Band row rr holds image row r0-11+rr; plane row R = rr-2 (image row r0-10+R) is complete at step rr.
+// Tap column t is cost column t-1 (cost column s uses tap columns s, s+1, s+2): left band column t+4, right band column
+// t-1+Lp-d for level d (same indexing as the cost phase of mbm_wta_fast.cu).  Lane .x = level d0, .y = level d0+1.
+// The 3x3 cost of the reference is a box sum of the tap field 255-|l-r|, and every window is a box sum of costs, so the
+// horizontal 3-tap commutes with everything done here: each |l-r| is formed ONCE (by the thread of its column) and summed
+// vertically; phase B applies the horizontal 3-tap together with its sliding window sums.
 __device__ __forceinline__ void screen_phase_a(const float *__restrict__ pl, const float *__restrict__ pr, int RW,
                                                float2 *__restrict__ bY, float2 *__restrict__ bZ, float2 *__restrict__ bW,
                                                bool keep_z, bool keep_w) {
@@ -80,26 +87,26 @@ __device__ __forceinline__ void screen_phase_a(const float *__restrict__ pl, con
     // the stages are listed last-first, so every instruction of an iteration only reads results of EARLIER
     // iterations (the loop is fully unrolled: all ring indices are compile-time, rings are just names).  Pair sums
     // (p, q, zb, wb) are formed as soon as their operands exist, which leaves one dependent add per stage:
-    //   E0 loads | E1 a = l-r | E3 u = |a0|+|a1| | E4 h3 = u+|a2| | E5 X | E6 Y3 | E7 Z9 | E8 W21
+    //   E0 loads | E1 a = l-r | E2 p, X | E3 q, Y3 | E4 zb, Z9, wb | E5 W21
     // The screen sums DISSIMILARITIES |l-r| (the abs is a free operand modifier) and phase B turns the window sums
     // into similarities: N*255 - sum|a| differs from the sum of the reference's taps fl(255-|a|) by at most N*255*u.
-    //   X(R)   = h3(R) + h3(R+1) + h3(R+2)              3x3 sum of plane row R (band rows R..R+2)
+    //   X(R)   = |a|(R) + |a|(R+1) + |a|(R+2)           3-row sum of this tap column at plane row R (band rows R..R+2)
     //   Y3(c)  = X(c-1) + X(c) + X(c+1)      c in [1,50]
     //   Z9(c)  = Y3(c-3) + Y3(c) + Y3(c+3)   c in [4,47]
     //   W21(c) = Z9(c-6) + Y3(c) + Z9(c+6)   c in [10,41]   (the 32 output rows of the tile are plane rows 10..41)
     constexpr int PF = 3;    // the band loads of a row are issued PF iterations before their first use
-    float rw[8][7];          // raw band values: l0 l1 l2 | q0 q1 q2 q3
-    float a[4][6];           // l - r per (tap column, level)
-    float2 u[4], h3[4], p[4], X[4], q[4];
+    float rw[8][3];          // raw band values: l | r(level d0+1) r(level d0)
+    float2 a[4];             // l - r per level
+    float2 p[4], X[4], q[4];
     float2 Y[16], Z[16], zb[16], wb[16];
 #pragma unroll
-    for (int it = 0; it < SBR + PF + 7; it++) {
-        {   // E8: row i delivered Z9(i-6) in the previous iteration -> W21(i-12)
-            const int i = it - PF - 6, cz = i - 6, cw = cz - 6;
+    for (int it = 0; it < SBR + PF + 5; it++) {
+        {   // E5: row i delivered Z9(i-6) in the previous iteration -> W21(i-12)
+            const int i = it - PF - 4, cz = i - 6, cw = cz - 6;
             if (i >= 0 && i < SBR && cw >= 10 && cw <= 41 && keep_w) bW[(cw - 10) * SPW] = add2(wb[cw % 16], Z[cz % 16]);
         }
-        {   // E7: row i delivered Y3(i-3) in the previous iteration
-            const int i = it - PF - 5, cy = i - 3;
+        {   // E4: row i delivered Y3(i-3) in the previous iteration
+            const int i = it - PF - 3, cy = i - 3;
             if (i >= 0 && i < SBR && cy >= 1) {
                 if (cy >= 7) {
                     const int cz = cy - 3;
@@ -110,8 +117,8 @@ __device__ __forceinline__ void screen_phase_a(const float *__restrict__ pl, con
                 if (cy >= 10 && cy <= 41) wb[cy % 16] = add2(Z[(cy - 6) % 16], Y[cy % 16]);   // Z9(cy-6) is 3 iterations old
             }
         }
-        {   // E6: row i delivered X(i-2) in the previous iteration
-            const int i = it - PF - 4, R = i - 2;
+        {   // E3: row i delivered X(i-2) in the previous iteration
+            const int i = it - PF - 2, R = i - 2;
             if (i >= 0 && i < SBR && R >= 0) {
                 if (R >= 2) {
                     const int cy = R - 1;
@@ -121,47 +128,30 @@ __device__ __forceinline__ void screen_phase_a(const float *__restrict__ pl, con
                 if (R >= 1) q[R % 4] = add2(X[(R - 1) % 4], X[R % 4]);
             }
         }
-        {   // E5: h3(i) is one iteration old
-            const int i = it - PF - 3;
-            if (i >= 0 && i < SBR) {
-                if (i >= 2) X[(i - 2) % 4] = add2(p[(i - 1) % 4], h3[i % 4]);
-                if (i >= 1) p[i % 4] = add2(h3[(i - 1) % 4], h3[i % 4]);
-            }
-        }
-        {   // E4: lane .x = level d0, .y = level d0+1
-            const int i = it - PF - 2;
-            if (i >= 0 && i < SBR) {
-                const float *aa = a[i % 4];
-                h3[i % 4] = make_float2(__fadd_rn(u[i % 4].x, fabsf(aa[4])), __fadd_rn(u[i % 4].y, fabsf(aa[5])));
-            }
-        }
-        {   // E3
+        {   // E2: a(i) is one iteration old; scalar adds, |.| is an operand modifier
             const int i = it - PF - 1;
             if (i >= 0 && i < SBR) {
-                const float *aa = a[i % 4];
-                u[i % 4] = make_float2(__fadd_rn(fabsf(aa[0]), fabsf(aa[2])), __fadd_rn(fabsf(aa[1]), fabsf(aa[3])));
+                const float2 ai = a[i % 4];
+                if (i >= 2) X[(i - 2) % 4] = make_float2(__fadd_rn(p[(i - 1) % 4].x, fabsf(ai.x)), __fadd_rn(p[(i - 1) % 4].y, fabsf(ai.y)));
+                if (i >= 1) {
+                    const float2 am = a[(i - 1) % 4];
+                    p[i % 4] = make_float2(__fadd_rn(fabsf(am.x), fabsf(ai.x)), __fadd_rn(fabsf(am.y), fabsf(ai.y)));
+                }
             }
         }
         {   // E1: the loads were issued PF iterations ago
             const int i = it - PF;
             if (i >= 0 && i < SBR) {
                 const float *w = rw[i % 8];
-                float *aa = a[i % 4];
-                aa[0] = __fsub_rn(w[0], w[4]); aa[1] = __fsub_rn(w[0], w[3]);
-                aa[2] = __fsub_rn(w[1], w[5]); aa[3] = __fsub_rn(w[1], w[4]);
-                aa[4] = __fsub_rn(w[2], w[6]); aa[5] = __fsub_rn(w[2], w[5]);
+                a[i % 4] = make_float2(__fsub_rn(w[0], w[2]), __fsub_rn(w[0], w[1]));
             }
         }
         if (it < SBR) {   // E0 (volatile asm keeps the loads where they are written, PF iterations ahead of their use)
             float *w = rw[it % 8];
             const unsigned la = smem_u32(pl + it * LW), ra = smem_u32(pr);
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w[0]) : "r"(la));
-            asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(w[1]) : "r"(la));
-            asm volatile("ld.shared.f32 %0, [%1+8];" : "=f"(w[2]) : "r"(la));
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w[3]) : "r"(ra));
-            asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(w[4]) : "r"(ra));
-            asm volatile("ld.shared.f32 %0, [%1+8];" : "=f"(w[5]) : "r"(ra));
-            asm volatile("ld.shared.f32 %0, [%1+12];" : "=f"(w[6]) : "r"(ra));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w[1]) : "r"(ra));
+            asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(w[2]) : "r"(ra));
             pr += RW;
         }
     }
@@ -292,46 +282,40 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
         __syncthreads();
 
         // ---- phase B ---------------------------------------------------------------------------------------
-        // Sliding sums along the row: the first window is a tree sum, every further output is one dependent add of
-        // a precomputed difference (entering - leaving cell), so the H and C recurrences are two short chains that
-        // interleave.  Absolute error of a window sum <= (5 + 2*15) u S_max (see the header).
+        // Sliding sums along the row: the first window is a tree sum, every further position is one dependent add of
+        // a precomputed difference (entering - leaving cell).  Absolute error of a window sum <= (5 + 2*17 + 2) u S_max
+        // (see the header).
         const float2 neg1 = make_float2(-1.0f, -1.0f);
-        float2 dh[16], dc[16], V[16];
-        {   // H: 21-column sum of Y3, cost columns y .. y+20 for tile column y
+        // Window sums over TAP columns: a cost-column window [c, c+n) is the tap-column window [c, c+n+2) with the
+        // horizontal 3-tap folded in, i.e. the sum of three n-wide box sums at consecutive positions.  Each n-wide sum
+        // slides (one dependent add of a precomputed difference per position); A' = (H' V') C' with similarities
+        // N*255 - dissimilarity sum.
+        float2 A[16];
+        {   // H: cost columns y .. y+20  ->  S21(p) = sum of Y3 over tap columns p .. p+20, H = S21(y) + S21(y+1) + S21(y+2)
             const float4 *pp = reinterpret_cast<const float4 *>(bY + row * SPY + 16 * seg);
-            float2 y[36];
+            float2 y[38];
 #pragma unroll
-            for (int j = 0; j < 18; j++) {
+            for (int j = 0; j < 19; j++) {
                 const float4 v4 = pp[j];
                 y[2 * j] = lo2(v4);
                 y[2 * j + 1] = hi2(v4);
             }
-            float2 s1[10], s2[5];
+            float2 s1[10], s2[5], S[18];
 #pragma unroll
             for (int j = 0; j < 10; j++) s1[j] = add2(y[2 * j], y[2 * j + 1]);
 #pragma unroll
             for (int j = 0; j < 5; j++) s2[j] = add2(s1[2 * j], s1[2 * j + 1]);
-            dh[0] = add2(add2(add2(s2[0], s2[1]), add2(s2[2], s2[3])), add2(s2[4], y[20]));
+            S[0] = add2(add2(add2(s2[0], s2[1]), add2(s2[2], s2[3])), add2(s2[4], y[20]));
 #pragma unroll
-            for (int k = 1; k < 16; k++) dh[k] = __ffma2_rn(y[k - 1], neg1, y[k + 20]);   // y[k+20] - y[k-1], one rounding
+            for (int k = 1; k < 18; k++) S[k] = add2(S[k - 1], __ffma2_rn(y[k - 1], neg1, y[k + 20]));   // + (y[k+20] - y[k-1])
+            const float2 hmax = make_float2(kHVmax, kHVmax);
+#pragma unroll
+            for (int k = 0; k < 16; k++) A[k] = __ffma2_rn(add2(add2(S[k], S[k + 1]), S[k + 2]), neg1, hmax);
         }
-        {   // C: 9-column sum of Z9, cost columns y+6 .. y+14 (buffer column = cost column - 6)
-            const float4 *pp = reinterpret_cast<const float4 *>(bZ + row * SPZ + 16 * seg);
-            float2 z[24];
-#pragma unroll
-            for (int j = 0; j < 12; j++) {
-                const float4 v4 = pp[j];
-                z[2 * j] = lo2(v4);
-                z[2 * j + 1] = hi2(v4);
-            }
-            dc[0] = add2(add2(add2(z[0], z[1]), add2(z[2], z[3])), add2(add2(z[4], z[5]), add2(add2(z[6], z[7]), z[8])));
-#pragma unroll
-            for (int k = 1; k < 16; k++) dc[k] = __ffma2_rn(z[k - 1], neg1, z[k + 8]);
-        }
-        {   // V: W21 of cost columns y+9, y+10, y+11 (buffer column = cost column - 8); as a similarity
+        {   // V: cost columns y+9 .. y+11 -> tap columns y+9 .. y+13 with weights 1 2 3 2 1 (buffer column = tap column - 9)
             const float4 *pp = reinterpret_cast<const float4 *>(bW + row * SPW + 16 * seg);
             const float2 vmax = make_float2(kHVmax, kHVmax);
-            float2 w[20];
+            float2 w[20], T[18];
 #pragma unroll
             for (int j = 0; j < 10; j++) {
                 const float4 v4 = pp[j];
@@ -339,20 +323,25 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
                 w[2 * j + 1] = hi2(v4);
             }
 #pragma unroll
-            for (int k = 0; k < 16; k++) V[k] = __ffma2_rn(add2(add2(w[k + 1], w[k + 2]), w[k + 3]), neg1, vmax);
-        }
-        float2 A[16];
-        {   // similarity sums = 255 * taps - dissimilarity sums; A' = (H' V') C'
-            const float2 hmax = make_float2(kHVmax, kHVmax), cmax = make_float2(kCmax, kCmax);
-            float2 h = dh[0], c = dc[0];
+            for (int k = 0; k < 18; k++) T[k] = add2(add2(w[k], w[k + 1]), w[k + 2]);
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                if (k) {
-                    h = add2(h, dh[k]);
-                    c = add2(c, dc[k]);
-                }
-                A[k] = __fmul2_rn(__fmul2_rn(__ffma2_rn(h, neg1, hmax), V[k]), __ffma2_rn(c, neg1, cmax));
+            for (int k = 0; k < 16; k++) A[k] = __fmul2_rn(A[k], __ffma2_rn(add2(add2(T[k], T[k + 1]), T[k + 2]), neg1, vmax));
+        }
+        {   // C: cost columns y+6 .. y+14 -> S9(p) = sum of Z9 over tap columns p+6 .. p+14 (buffer column = tap column - 6)
+            const float4 *pp = reinterpret_cast<const float4 *>(bZ + row * SPZ + 16 * seg);
+            float2 z[26], S[18];
+#pragma unroll
+            for (int j = 0; j < 13; j++) {
+                const float4 v4 = pp[j];
+                z[2 * j] = lo2(v4);
+                z[2 * j + 1] = hi2(v4);
             }
+            S[0] = add2(add2(add2(z[0], z[1]), add2(z[2], z[3])), add2(add2(z[4], z[5]), add2(add2(z[6], z[7]), z[8])));
+#pragma unroll
+            for (int k = 1; k < 18; k++) S[k] = add2(S[k - 1], __ffma2_rn(z[k - 1], neg1, z[k + 8]));
+            const float2 cmax = make_float2(kCmax, kCmax);
+#pragma unroll
+            for (int k = 0; k < 16; k++) A[k] = __fmul2_rn(A[k], __ffma2_rn(add2(add2(S[k], S[k + 1]), S[k + 2]), neg1, cmax));
         }
         // ---- candidate bookkeeping: the set always contains every LEVEL within kKeep of the final maximum -----------
         const bool has2 = (d0 + 1 < L);
