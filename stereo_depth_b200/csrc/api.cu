@@ -203,22 +203,6 @@ bool screen_allowed(const sd_handle *h) {
            !h->dbg_agg && (!h->s.agg_vol || h->s.gather_mask) && mbm_screen_supported(h->g);
 }
 
-// Does the screen pay for a launch of `frames` frames?  Behind the screen a launch cannot finish before its heaviest
-// tile has (a tile that keeps all its level pairs costs as much as an unscreened one), so with less than about two
-// waves of tiles the unscreened kernel is faster.  Model in units of one full tile: unscreened = waves; screened =
-// screen kernel (0.215 tile-times per tile and SM) + max(1 heavy tile, 25 % of the work spread over all slots).
-// With variant 0 only; an explicit variant 2 always screens (tests, tuning).
-bool screen_pays(const sd_handle *h, int frames) {
-    if (h->variant == 2) return true;
-    const PadGeom pg = make_pad_geom(h->g.Hd, h->g.Wd, h->g.L, h->g.min_ds);
-    const double tiles = (double)pg.tiles_x * pg.tiles_y * frames, sms = h->sms, slots = (double)h->sms * h->per_sm_fast;
-    const double unscreened = (double)(long long)((tiles + slots - 1) / slots);
-    const double screened = tiles * 0.215 / sms + (0.25 * tiles / slots > 1.0 ? 0.25 * tiles / slots : 1.0);
-    return screened < 0.95 * unscreened;
-}
-
-bool screen_active(const sd_handle *h, int frames) { return screen_allowed(h) && screen_pays(h, frames); }
-
 // LEVEL SPLIT of the unscreened specialised kernel for launches that do not fill the GPU (single frames, thin row
 // bands): a tile's L/2 level pairs go to `split` blocks, so a launch of T tiles has T*split blocks of L/(2 split)
 // passes each instead of T blocks of L/2.  Cost model in pass-times of one block: rounds * (passes + ~1.5 for staging
@@ -245,6 +229,45 @@ int plan_split(const sd_handle *h, int frames, bool need_buffers, double *cost_o
     return best;
 }
 
+// Level split behind the screen: a launch cannot finish before its heaviest tile has, and a tile that keeps all its level
+// pairs costs as much as an unscreened one.  With fewer than about four waves of tiles every tile's flagged pairs are
+// therefore spread over several blocks (by rank; mbm_wta_fast.cu), heaviest tiles first.
+int screened_split(const sd_handle *h, int frames) {
+    if (h->split_off || !h->s.wta4_parts) return 1;
+    const PadGeom pg = make_pad_geom(h->g.Hd, h->g.Wd, h->g.L, h->g.min_ds);
+    const long long tiles = (long long)pg.tiles_x * pg.tiles_y * frames, slots = (long long)h->sms * h->per_sm_fast;
+    if (tiles >= 4 * slots) return 1;
+    int S = (int)((4 * slots + tiles - 1) / tiles);
+    const int M = ((h->g.L + 1) & ~1) / 2;
+    if (S > 8) S = 8;
+    if (S > M) S = M;
+    while (S > 1 && (size_t)S * frames * h->g.Hd * h->g.Wd > h->parts_capacity) S--;
+    return S < 1 ? 1 : S;
+}
+
+// Does the screen pay for a launch of `frames` frames?  Model in units of one full (unscreened) tile: unscreened = waves;
+// screened = screen kernel (0.175 tile-times per tile and SM, at least one tile's worth) + exact kernel
+// max(heaviest tile / split, 25 % of the work spread over all slots).  With variant 0 only; an explicit variant 2 always
+// screens (tests, tuning).
+bool screen_pays(const sd_handle *h, int frames) {
+    if (h->variant == 2) return true;
+    const PadGeom pg = make_pad_geom(h->g.Hd, h->g.Wd, h->g.L, h->g.min_ds);
+    const double tiles = (double)pg.tiles_x * pg.tiles_y * frames, sms = h->sms, slots = (double)h->sms * h->per_sm_fast;
+    // best unscreened alternative: the split two-phase kernel (plan_split) or whole waves
+    double unscreened = (double)(long long)((tiles + slots - 1) / slots);
+    {
+        const int M = ((h->g.L + 1) & ~1) / 2;
+        double c = 0.0;
+        if (plan_split(h, frames, true, &c) > 1 && c / (M + kSplitOverhead) < unscreened) unscreened = c / (M + kSplitOverhead);
+    }
+    const double heavy = 1.0 / screened_split(h, frames) + 0.05;
+    const double spread = 0.25 * tiles / slots;
+    const double screen_kernel = tiles * 0.175 / sms > 0.175 ? tiles * 0.175 / sms : 0.175;
+    return screen_kernel + (spread > heavy ? spread : heavy) < 0.95 * unscreened;
+}
+
+bool screen_active(const sd_handle *h, int frames) { return screen_allowed(h) && screen_pays(h, frames); }
+
 // 1 generic, 2 specialised, 3 warp-specialised -- for a launch of `frames` frames
 int active_variant(const sd_handle *h, int frames) {
     const bool fast = h->s.padl && ((h->variant >= 2) || (h->variant == 0 && mbm_wta_fast_supported(h->g)));
@@ -264,7 +287,8 @@ int active_variant(const sd_handle *h, int frames) {
 
 // level split of the next launch of `frames` frames (1 = off): only for the unscreened specialised kernel
 int active_split(const sd_handle *h, int frames) {
-    if (h->split_off || active_variant(h, frames) != 2 || screen_active(h, frames)) return 1;
+    if (h->split_off || active_variant(h, frames) != 2) return 1;
+    if (screen_active(h, frames)) return h->s.agg_vol ? 1 : screened_split(h, frames);   // (not in reference-compat mode)
     return plan_split(h, frames, true, nullptr);
 }
 
@@ -309,7 +333,9 @@ int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int 
             SD_CUDA(h, launch_abs_targets(h->g, frames, h->s, st));
             SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, nullptr, nullptr, st, false, true));
         } else if (v == 2) {
-            const int split = screen ? 1 : active_split(h, frames);
+            // (a paused screen falls back to the unscreened plan for this launch)
+            const int split = h->split_off ? 1 : (screen ? (h->s.agg_vol ? 1 : screened_split(h, frames))
+                                                          : plan_split(h, frames, true, nullptr));
             SD_CUDA(h, launch_mbm_wta_fast(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st, screen, false, split));
         }
         else SD_CUDA(h, launch_mbm_wta_generic(h->g, frames, h->s, h->dbg_cost, h->dbg_agg, st));
@@ -479,14 +505,25 @@ int sd_create(const sd_config *cfg, int device, int frames_per_launch, sd_handle
         SD_CUDA(h, scratch_alloc(h, (void **)&h->s.range_flag, sizeof(int)));
         SD_CUDA(h, cudaMemset(h->s.range_flag, 0, sizeof(int)));
         {   // part slots for level-split launches: sized for the largest split any launch size of this handle would pick
+            // (unscreened: plan_split; behind the screen: up to 8 parts while the launch has fewer than four waves of tiles)
+            const long long slots = (long long)h->sms * h->per_sm_fast;
+            const long long tiles1 = (long long)pg.tiles_x * pg.tiles_y;
             size_t need = 0;
+            int max_split = 1;
             for (int f = 1; f <= h->chunk; f++) {
-                const int S = plan_split(h, f, false, nullptr);
+                int S = plan_split(h, f, false, nullptr);
+                if (mbm_screen_supported(g) && tiles1 * f < 4 * slots) {
+                    int Ss = (int)((4 * slots + tiles1 * f - 1) / (tiles1 * f));
+                    Ss = Ss > 8 ? 8 : Ss;
+                    if (Ss > S) S = Ss;
+                }
+                if (S > max_split) max_split = S;
                 if (S > 1 && (size_t)S * f * nd > need) need = (size_t)S * f * nd;
             }
             if (need > 0 && need * (sizeof(float4) + sizeof(float2)) <= ((size_t)1 << 30)) {
                 SD_CUDA(h, scratch_alloc(h, (void **)&h->s.wta4_parts, need * sizeof(float4)));
                 SD_CUDA(h, scratch_alloc(h, (void **)&h->s.edge2_parts, need * sizeof(float2)));
+                SD_CUDA(h, scratch_alloc(h, (void **)&h->s.part_range, (size_t)kMaxSplit * F * tiles1 * sizeof(int2)));
                 h->parts_capacity = need;
             }
         }
@@ -538,6 +575,7 @@ int sd_destroy(sd_handle *h) {
         scratch_free(h, h->s.refined);
         scratch_free(h, h->s.wta4_parts);
         scratch_free(h, h->s.edge2_parts);
+        scratch_free(h, h->s.part_range);
         if (h->ev_last) cudaEventDestroy(h->ev_last);
         scratch_free(h, h->s.agg_vol);
         scratch_free(h, h->s.padl);

@@ -94,6 +94,7 @@ struct Scratch {
     float *refined;
     float4 *wta4_parts;   // [split][frames][Hd*Wd] part slots of a level-split launch (small launches only), else NULL
     float2 *edge2_parts;  // [split][frames][Hd*Wd]
+    int2 *part_range;     // [split][frames*tiles] first / last level each part evaluated (-1: empty part)
     float *agg_vol;  // [F][L][Hd*Wd] (plane-major) aggregated volume, only in reference-compat mode (abs_index), else NULL
     float *padl, *padr;  // [F][rows][pwl], [F][rows][pwr] wrap-padded pooled planes (PadGeom), NULL if unsupported
     // Certified level screen (mbm_screen.cu), all NULL when unsupported:

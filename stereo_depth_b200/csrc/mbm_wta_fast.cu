@@ -59,7 +59,7 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
                     float4 *__restrict__ wta4, float2 *__restrict__ edge2, float *__restrict__ dbg_cost,
                     float *__restrict__ dbg_agg, float *__restrict__ agg_planes, const unsigned *__restrict__ pass_mask,
                     const int *__restrict__ range_flag, int range_epoch, const int *__restrict__ tile_order,
-                    const int *__restrict__ bucket_count, int n_split) {
+                    const int *__restrict__ bucket_count, int n_split, int2 *__restrict__ part_range) {
     using C = Cfg<BH>;
     extern __shared__ float4 smem4[];
     float4 *plane = smem4;                                              // [PRW][42] chunks of (cell,level) pairs
@@ -67,12 +67,19 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
     float *bandR = bandL + C::BR * LW;                                  // [BR][RW]
 
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    // Which tile: by default the block's own coordinates.  Behind the level screen the tiles differ widely in cost
+    // Which tile: by default the blocks in launch order.  Behind the level screen the tiles differ widely in cost
     // (3 .. M level pairs), so the screen sorts them into 8 buckets by pair count and blocks take them heaviest first
     // (longest-processing-time order: no long tile is left to start last).
-    int tile = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    // LEVEL SPLIT (launches too small to fill the GPU: single frames, thin row bands): gridDim.z = frames * n_split and
+    // consecutive blocks are the parts of one tile.  Part p evaluates the p-th share of the tile's flagged level pairs
+    // (by rank, ascending) into the p-th slot of the part arrays (wta4 / edge2 then point at [n_split][frames][Hd*Wd]) and
+    // notes the first / last level it evaluated in part_range; merge_parts_kernel combines the slots.
+    // n_split == 1: every flagged pair, final arrays.
+    const int lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const int part = lin % n_split;
+    const int n_tiles = gridDim.x * gridDim.y * (gridDim.z / n_split);   // tiles of the launch (all frames)
+    int tile = lin / n_split;
     if (tile_order) {
-        const int nt = gridDim.x * gridDim.y * gridDim.z;
         int cnt[kScreenBuckets];
 #pragma unroll
         for (int b = 0; b < kScreenBuckets; b++) cnt[b] = __ldg(bucket_count + b);   // independent loads, one round trip
@@ -81,7 +88,7 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
 #pragma unroll
         for (int b = kScreenBuckets - 1; b >= 0; b--) {
             if (!found && rem < cnt[b]) {
-                slot = b * nt + rem;
+                slot = b * n_tiles + rem;
                 found = true;
             }
             if (!found) rem -= cnt[b];
@@ -89,14 +96,9 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
         if (found) tile = tile_order[slot];
     }
     const int tile_x = tile % gridDim.x, tile_y = (tile / gridDim.x) % gridDim.y;
-    // LEVEL SPLIT (small launches: single frames, thin row bands): gridDim.z = frames * n_split, and this block evaluates
-    // only the level pairs [m_begin, m_end) of its tile into the part-th slot of the part arrays (wta4 / edge2 then point
-    // at [n_split][frames][Hd*Wd]); merge_parts_kernel combines the slots.  n_split == 1: the whole range, final arrays.
-    const int zf = tile / (gridDim.x * gridDim.y);
-    const int frame = zf / n_split, part = zf - frame * n_split, r0 = tile_y * BH, c0 = tile_x * BW;
+    const int frame = tile / (gridDim.x * gridDim.y), r0 = tile_y * BH, c0 = tile_x * BW;
     const int Hd = g.Hd, Wd = g.Wd, L = g.L;
     const int Lp = (L + 1) & ~1, M = Lp >> 1;
-    const int m_begin = (part * M) / n_split, m_end = ((part + 1) * M) / n_split;
     const size_t np = (size_t)Hd * Wd;
     const int RW = pg.rw;
 
@@ -113,9 +115,23 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
         // (gather pass: the masks are exact requests, not a screen result -- they hold whatever the range flag says)
         if (pass_mask && (STORE == 2 || *range_flag != range_epoch))
             w = pass_mask[(size_t)tile * 4 + tid];
-        s_pass[tid] = w;
+        const int valid_bits = M - 32 * tid;   // only pairs 0 .. M-1 exist
+        s_pass[tid] = valid_bits >= 32 ? w : (valid_bits > 0 ? (w & ((1u << valid_bits) - 1u)) : 0u);
     }
     __syncthreads();
+    // this part's share of the flagged pairs, by rank
+    const int n_flag = __popc(s_pass[0]) + __popc(s_pass[1]) + __popc(s_pass[2]) + __popc(s_pass[3]);
+    const int r_begin = (part * n_flag) / n_split, r_end = ((part + 1) * n_flag) / n_split;
+    const int px0 = r0 + 4 * ty, py0 = c0 + 4 * tx;  // first owned pixel
+    const size_t o00 = ((size_t)part * (gridDim.z / n_split) + frame) * np + (size_t)px0 * Wd + py0;
+    if (n_split > 1 && r_begin == r_end) {
+        // nothing to do for this part (fewer flagged pairs than parts): "no maximum here" records, empty range
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            if (px0 + (k >> 2) < Hd && py0 + (k & 3) < Wd) wta4[o00 + (size_t)(k >> 2) * Wd + (k & 3)] = make_float4(-1.0f, 0.0f, 0.0f, 0.0f);
+        if (tid == 0) part_range[(size_t)part * n_tiles + tile] = make_int2(-1, -1);
+        return;
+    }
     if (tid < 32) {
         if (tid == 0) mbar_expect_tx(&band_bar, (unsigned)(C::BR * (LW + RW) * 4));
         __syncwarp();
@@ -132,8 +148,6 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
     // improves, its record (d*, A[d*-1], A[d*], A[d*+1]) is (re)written to HBM/L2 -- about ln(L) times per
     // pixel -- which keeps ~50 registers free for the adder chains.  Pixels outside the image start at
     // +inf and therefore never store.
-    const int px0 = r0 + 4 * ty, py0 = c0 + 4 * tx;  // first owned pixel
-    const size_t o00 = ((size_t)part * (gridDim.z / n_split) + frame) * np + (size_t)px0 * Wd + py0;
     float best[16], prev[16];
     unsigned pend = 0;  // bit k: record k still waits for A[d*+1] (arrives with the next pass)
 #pragma unroll
@@ -153,10 +167,17 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
             if (++spins > (1 << 24)) __trap();  // a lost transaction must not hang the GPU
     }
 
-    for (int m = m_begin; m < m_end; m++) {
+    int rank = 0, m_first = -1, m_last = -1;
+    for (int m = 0; m < M; m++) {
         // Skipped level pairs leave prev[] / pend stale.  That only ever reaches records that a later level
-        // overwrites: the reference's arg-max d* is always evaluated together with d*-1 and d*+1 (circular).
+        // overwrites: the reference's arg-max d* is always evaluated together with d*-1 and d*+1 (circular), and
+        // adjacent flagged pairs that fall into different parts are joined by merge_parts_kernel.
         if (!((s_pass[(m >> 5) & 3] >> (m & 31)) & 1u)) continue;
+        if (rank++ < r_begin) continue;
+        if (rank > r_end) break;
+        const bool first_pass = (m_first < 0);
+        if (first_pass) m_first = m;
+        m_last = m;
         const int d0 = 2 * m;
         // ================= cost phase: plane[R][s] = (cost(d0), cost(d0+1)) ==========================
         // The right band is read at column offset e = Lp-2-d0 (even): 16-byte aligned on every other
@@ -389,11 +410,9 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
             }
         }
         if (STORE == 2) {
-            // gather pass: pair m is the rank-th flagged pair of this tile; its two levels go to
+            // gather pass: pair m is the (rank-1)-th flagged pair of this tile; its two levels go to
             // agg_planes[tile][rank][level parity][32*64] -- one coalesced 16-byte store per thread row and level
-            int rank = __popc(s_pass[m >> 5] & ((1u << (m & 31)) - 1u));
-            for (int w = 0; w < (m >> 5); w++) rank += __popc(s_pass[w]);
-            float *q0 = agg_planes + ((size_t)tile * M + rank) * (2 * BH * BW) + (4 * ty) * BW + 4 * tx;
+            float *q0 = agg_planes + ((size_t)tile * M + (rank - 1)) * (2 * BH * BW) + (4 * ty) * BW + 4 * tx;
 #pragma unroll
             for (int a = 0; a < 4; a++) {
                 *reinterpret_cast<float4 *>(q0 + a * BW) = make_float4(hv[a * 4].x, hv[a * 4 + 1].x, hv[a * 4 + 2].x, hv[a * 4 + 3].x);
@@ -427,13 +446,13 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
                 }
             }
         }
-        if (m == m_begin) {
+        if (first_pass) {
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 const int x = px0 + (k >> 2), y = py0 + (k & 3);
                 if (x < Hd && y < Wd) {
                     const size_t o = o00 + (size_t)(k >> 2) * Wd + (k & 3);
-                    edge2[o].x = hv[k].x;                                    // A[0] (first level of this part)
+                    edge2[o].x = hv[k].x;                                    // A[first level this part evaluates] (A[0] unsplit)
                     // record if nothing ever beats FLT_MIN; in a part slot d = -1 says "no maximum in this range"
                     wta4[o] = make_float4(n_split > 1 ? -1.0f : 0.0f, 0.0f, hv[k].x, hv[k].y);
                 }
@@ -466,21 +485,31 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         const int x = px0 + (k >> 2), y = py0 + (k & 3);
-        if (x < Hd && y < Wd) edge2[o00 + (size_t)(k >> 2) * Wd + (k & 3)].y = prev[k];  // A[L-1] (last level of this part)
+        if (x < Hd && y < Wd) edge2[o00 + (size_t)(k >> 2) * Wd + (k & 3)].y = prev[k];  // A[last level evaluated] (A[L-1] unsplit)
     }
+    if (n_split > 1 && tid == 0) part_range[(size_t)part * n_tiles + tile] = make_int2(2 * m_first, 2 * m_last + 1);
 }
 
 // Combines the part slots of a level-split launch into the final records: the maximum over the parts in ascending level
-// order with strict '>' (the first maximum wins, wta_disparity_selection.cu:22-29), its neighbours A[d*-1] / A[d*+1] taken
-// from the adjacent part's edge values when d* sits on a part boundary, and (A[0], A[L-1]) from the outermost parts.
-__global__ void merge_parts_kernel(const float4 *__restrict__ pw, const float2 *__restrict__ pe, float4 *__restrict__ wta4,
-                                   float2 *__restrict__ edge2, size_t n, int S, int M) {
+// order with strict '>' (the first maximum wins, wta_disparity_selection.cu:22-29).  Its neighbours A[d*-1] / A[d*+1] come
+// from the adjacent part's edge values when d* is the first / last level its part evaluated: the pairs holding d*-1 and
+// d*+1 are always flagged, so they are the last pair of the previous part / the first pair of the next one.
+// (A[0], A[L-1]) for the circular wrap come from the outermost non-empty parts.
+__global__ void merge_parts_kernel(const float4 *__restrict__ pw, const float2 *__restrict__ pe, const int2 *__restrict__ part_range,
+                                   float4 *__restrict__ wta4, float2 *__restrict__ edge2, int Hd, int Wd, int frames, int S,
+                                   int tiles_x, int tiles_y) {
+    const size_t np = (size_t)Hd * Wd, n = np * frames;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const int frame = (int)(i / np), x = (int)((i % np) / Wd), y = (int)(i % Wd);
+    const size_t tile = ((size_t)frame * tiles_y + x / kTileH) * tiles_x + y / kTileW, n_tiles = (size_t)frames * tiles_x * tiles_y;
     float best = kFltMin;
-    float4 out = pw[i];
-    int wp = -1;
+    float4 out = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    int wp = -1, p_first = -1, p_last = -1;
     for (int p = 0; p < S; p++) {
+        if (part_range[(size_t)p * n_tiles + tile].x < 0) continue;   // empty part
+        if (p_first < 0) p_first = p;
+        p_last = p;
         const float4 r = pw[(size_t)p * n + i];
         if (r.x >= 0.0f && r.z > best) {
             best = r.z;
@@ -489,14 +518,29 @@ __global__ void merge_parts_kernel(const float4 *__restrict__ pw, const float2 *
         }
     }
     if (wp < 0) {
-        out = make_float4(0.0f, 0.0f, out.z, out.w);   // nothing beats FLT_MIN: level 0, (A[0], A[1]) like the unsplit kernel
+        // nothing beats FLT_MIN: level 0 with (A[0], A[1]) like the unsplit kernel (the first part's first pair)
+        const float4 r0 = pw[(size_t)(p_first < 0 ? 0 : p_first) * n + i];
+        out = make_float4(0.0f, 0.0f, r0.z, r0.w);
     } else {
-        const int d = (int)out.x, l0 = 2 * ((wp * M) / S), l1 = 2 * (((wp + 1) * M) / S) - 1;
-        if (d == l0 && wp > 0) out.y = pe[(size_t)(wp - 1) * n + i].y;
-        if (d == l1 && wp < S - 1) out.w = pe[(size_t)(wp + 1) * n + i].x;
+        const int2 rg = part_range[(size_t)wp * n_tiles + tile];
+        const int d = (int)out.x;
+        if (d == rg.x) {   // A[d*-1] is the previous non-empty part's last level
+            for (int p = wp - 1; p >= 0; p--)
+                if (part_range[(size_t)p * n_tiles + tile].x >= 0) {
+                    out.y = pe[(size_t)p * n + i].y;
+                    break;
+                }
+        }
+        if (d == rg.y) {   // A[d*+1] is the next non-empty part's first level
+            for (int p = wp + 1; p < S; p++)
+                if (part_range[(size_t)p * n_tiles + tile].x >= 0) {
+                    out.w = pe[(size_t)p * n + i].x;
+                    break;
+                }
+        }
     }
     wta4[i] = out;
-    edge2[i] = make_float2(pe[i].x, pe[(size_t)(S - 1) * n + i].y);
+    if (p_first >= 0) edge2[i] = make_float2(pe[(size_t)p_first * n + i].x, pe[(size_t)p_last * n + i].y);
 }
 
 template <int BH, bool DBG, int MODE, int STORE>
@@ -511,26 +555,26 @@ cudaError_t launch_t(const Geom &g, int frames, const Scratch &s, float *dbg_cos
     if (STORE == 2) {
         mbm_wta_fast_kernel<BH, DBG, MODE, STORE><<<grid, Cfg<BH>::NT, smem, st>>>(
             g, pg, s.padl, s.padr, s.wta4, s.edge2, nullptr, nullptr, s.agg_vol, s.gather_mask, s.range_flag, s.range_epoch,
-            nullptr, s.bucket_count, 1);
+            nullptr, s.bucket_count, 1, nullptr);
         return cudaGetLastError();
     }
     if (split > 1) {
-        // level split: every tile's level pairs are spread over `split` blocks writing part slots, then merged
-        if (use_screen || STORE != 0 || DBG || !s.wta4_parts || !s.edge2_parts) return cudaErrorNotSupported;
+        // level split: every tile's flagged level pairs are spread over `split` blocks writing part slots, then merged
+        if (STORE != 0 || DBG || !s.wta4_parts || !s.edge2_parts || !s.part_range) return cudaErrorNotSupported;
         grid.z = frames * split;
         mbm_wta_fast_kernel<BH, DBG, MODE, STORE><<<grid, Cfg<BH>::NT, smem, st>>>(
-            g, pg, s.padl, s.padr, s.wta4_parts, s.edge2_parts, nullptr, nullptr, nullptr, nullptr, s.range_flag, s.range_epoch,
-            nullptr, s.bucket_count, split);
+            g, pg, s.padl, s.padr, s.wta4_parts, s.edge2_parts, nullptr, nullptr, nullptr, use_screen ? s.pass_mask : nullptr,
+            s.range_flag, s.range_epoch, use_screen ? s.tile_order : nullptr, s.bucket_count, split, s.part_range);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         const size_t n = (size_t)frames * g.Hd * g.Wd;
-        merge_parts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s.wta4_parts, s.edge2_parts, s.wta4, s.edge2, n, split,
-                                                                      ((g.L + 1) & ~1) / 2);
+        merge_parts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s.wta4_parts, s.edge2_parts, s.part_range, s.wta4, s.edge2,
+                                                                      g.Hd, g.Wd, frames, split, pg.tiles_x, pg.tiles_y);
         return cudaGetLastError();
     }
     mbm_wta_fast_kernel<BH, DBG, MODE, STORE><<<grid, Cfg<BH>::NT, smem, st>>>(
         g, pg, s.padl, s.padr, s.wta4, s.edge2, dbg_cost, dbg_agg, s.agg_vol, use_screen ? s.pass_mask : nullptr,
-        s.range_flag, s.range_epoch, use_screen ? s.tile_order : nullptr, s.bucket_count, 1);
+        s.range_flag, s.range_epoch, use_screen ? s.tile_order : nullptr, s.bucket_count, 1, nullptr);
     return cudaGetLastError();
 }
 

@@ -357,16 +357,19 @@ def test_batches_chunks_and_host_path_agree():
     assert mismatch(host.numpy(), singles) == 0
     assert mismatch(f32, singles) == 0
     assert mismatch(singles[4], ref) == 0
-    # 6 kernels per chunk (gray+pool, plane padding, level screen, cost+agg+WTA, secondary, fill), 3 chunks
-    assert be.native.screen_active and be.native.launches_per_call(n) == 6 * 3
+    # launches this small spread every tile's level pairs over several blocks (level split) + 1 merge kernel per chunk:
+    # gray+pool, plane padding, level screen, cost+agg+WTA, merge, secondary, fill -- 3 chunks
+    assert be.native.screen_active and be.native.level_split(3) > 1 and be.native.launches_per_call(n) == 7 * 3
     be.native.set_screen(False)
-    # unscreened launches this small split every tile's levels over several blocks: + 1 merge kernel per chunk
     assert be.native.level_split(3) > 1 and be.native.launches_per_call(n) == 6 * 3
+    assert mismatch(be.process_batch(torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()).cpu().numpy(), singles) == 0
     be.native.set_level_split(False)
     assert be.native.level_split(3) == 1 and be.native.launches_per_call(n) == 5 * 3
     assert mismatch(be.process_batch(torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()).cpu().numpy(), singles) == 0
-    be.native.set_level_split(True)
+    be.native.set_screen(True)
+    assert be.native.launches_per_call(n) == 6 * 3
     assert mismatch(be.process_batch(torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()).cpu().numpy(), singles) == 0
+    be.native.set_level_split(True)
 
 
 def test_reference_api_semantics():
@@ -576,17 +579,20 @@ def test_level_split_equals_unsplit(shape):
     L = mx // K + 1
     sm = cuda_depth.StereoMatching(cuda_depth.StereoMatchingConfiguration(**kw), frames_per_launch=1)
     sm.set_variant("fast")
-    sm.set_screen(False) if 3 <= L <= 128 else None
     lt, rt = torch.from_numpy(l).cuda(), torch.from_numpy(r).cuda()
-    outs = {}
-    for split in (True, False):
-        sm.set_level_split(split)
-        assert (sm.level_split(1) > 1) == (split and L >= 4), (split, sm.level_split(1))
-        out = sm.compute_disparity_map(lt, rt).cpu().numpy().copy()
-        outs[split] = {st: sm.stage(st).cpu().numpy() for st in ("wta", "agg3", "refined")}
-        outs[split]["out"] = out
-        for st in ("wta", "agg3", "refined", "out"):
-            assert mismatch(outs[split][st], ref[st]) == 0, (st, split, sm.level_split(1))
+    for screen in ((True, False) if 3 <= L <= 128 else (None,)):
+        if screen is not None:
+            sm.set_screen(screen)     # behind the screen the parts share a tile's FLAGGED pairs by rank
+        for split in (True, False):
+            sm.set_level_split(split)
+            assert (sm.level_split(1) > 1) == (split and L >= 4), (split, sm.level_split(1))
+            out = sm.compute_disparity_map(lt, rt).cpu().numpy().copy()
+            got = {st: sm.stage(st).cpu().numpy() for st in ("wta", "agg3", "refined")}
+            got["out"] = out
+            for st in ("wta", "agg3", "refined", "out"):
+                assert mismatch(got[st], ref[st]) == 0, (st, screen, split, sm.level_split(1))
+    if 3 <= L <= 128:
+        sm.set_screen(False)
     # out-of-range floats: every aggregated cost is negative, nothing beats FLT_MIN -> level 0 in every part
     sm.set_level_split(True)
     rng = np.random.default_rng(5)

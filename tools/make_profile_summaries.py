@@ -8,21 +8,22 @@ import shutil
 import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+R = os.environ.get("ROUND", "r02")   # file-name prefix of the round being summarised
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-shutil.copy(os.path.join(G, "launches.csv"), os.path.join(P, "r01_ncu_launches_bench_c3.csv"))
-shutil.copy(os.path.join(G, "bench.json"), os.path.join(P, "r01_bench_c3_1gpu.json"))
-shutil.copy(os.path.join(G, "bench_reference.json"), os.path.join(P, "r01_bench_reference_c3.json"))
-with open(os.path.join(P, "r01_ncu_kernelB_summary.txt"), "w") as f:
+shutil.copy(os.path.join(G, "launches.csv"), os.path.join(P, R + "_ncu_launches_bench_c3.csv"))
+shutil.copy(os.path.join(G, "bench.json"), os.path.join(P, R + "_bench_c3_1gpu.json"))
+shutil.copy(os.path.join(G, "bench_reference.json"), os.path.join(P, R + "_bench_reference_c3.json"))
+with open(os.path.join(P, R + "_ncu_kernelB_summary.txt"), "w") as f:
     subprocess.run(["python", os.path.join(ROOT, "tools", "ncu_phase_report.py"), os.path.join(G, "prof_kernelB.ncu-rep")], stdout=f)
-for rep, out in (("prof_screen.ncu-rep", "r01_ncu_screen_summary.txt"), ("prof_kernelB_screened.ncu-rep", "r01_ncu_kernelB_screened_summary.txt")):
+for rep, out in (("prof_screen.ncu-rep", R + "_ncu_screen_summary.txt"), ("prof_kernelB_screened.ncu-rep", R + "_ncu_kernelB_screened_summary.txt")):
     with open(os.path.join(P, out), "w") as f:
         subprocess.run(["python", os.path.join(ROOT, "tools", "ncu_phase_report.py"), os.path.join(G, rep)], stdout=f)
-for rep, out in (("prof_kernelB.ncu-rep", "r01_ncu_kernelB_details.txt"), ("prof_others.ncu-rep", "r01_ncu_other_kernels_details.txt"),
-                 ("prof_screen.ncu-rep", "r01_ncu_screen_details.txt")):
+for rep, out in (("prof_kernelB.ncu-rep", R + "_ncu_kernelB_details.txt"), ("prof_others.ncu-rep", R + "_ncu_other_kernels_details.txt"),
+                 ("prof_screen.ncu-rep", R + "_ncu_screen_details.txt")):
     with open(os.path.join(P, out), "w") as f:
         subprocess.run(["ncu", "-i", os.path.join(G, rep), "--page", "details"], stdout=f, stderr=subprocess.DEVNULL)
 
-lines = [l for l in open(os.path.join(P, "r01_ncu_launches_bench_c3.csv")) if not l.startswith("==")]
+lines = [l for l in open(os.path.join(P, R + "_ncu_launches_bench_c3.csv")) if not l.startswith("==")]
 agg = collections.defaultdict(list)
 for row in csv.DictReader(lines):
     if row.get("Metric Name") == "gpu__time_duration.sum":
@@ -33,7 +34,7 @@ out = ["ncu --metrics gpu__time_duration.sum --clock-control none -c 400, comman
        "(per-launch times are cold-cache and serialised: compare SHARES with bench.py's live roofline.share_of_step)", ""]
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     out.append(f"{k:42s} launches={len(v):4d} mean={sum(v) / len(v):9.1f} us  share={sum(v) / tot:.4f}")
-open(os.path.join(P, "r01_ncu_launch_shares.txt"), "w").write("\n".join(out) + "\n")
+open(os.path.join(P, R + "_ncu_launch_shares.txt"), "w").write("\n".join(out) + "\n")
 print("\n".join(out))
 
 raw = subprocess.run(["ncu", "-i", os.path.join(G, "prof_others.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -48,7 +49,7 @@ for d in rows[2:]:
     txt.append(d[idx[0]].split("(")[0])
     for i in idx[1:]:
         txt.append(f"    {hdr[i]:70s} {d[i]} {units[i]}")
-open(os.path.join(P, "r01_ncu_other_kernels_summary.txt"), "w").write("\n".join(txt) + "\n")
+open(os.path.join(P, R + "_ncu_other_kernels_summary.txt"), "w").write("\n".join(txt) + "\n")
 
 raw = subprocess.run(["ncu", "-i", os.path.join(G, "prof_kernelB.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
@@ -75,8 +76,8 @@ for rep in ("prof_screen.ncu-rep", "prof_kernelB_screened.ncu-rep"):
             screen_ncu[key] = float(d[hdr.index(name)])
 json.dump({"C3_per_frame": t / 8, "C3_screened_per_frame": ts / 8, "screen_kernel_ncu": screen_ncu,
            "note": "(dram__bytes_read.sum + dram__bytes_write.sum) / 8 of one launch over 8 frames of C3 (ncu --set full): C3_per_frame = "
-                   "mbm_wta_fast_kernel evaluating all levels (profiles/r01_ncu_kernelB_summary.txt); C3_screened_per_frame = mbm_screen_kernel + "
-                   "mbm_wta_fast_kernel behind the screen (r01_ncu_screen_summary.txt, r01_ncu_kernelB_screened_summary.txt); bench.py scales it by "
+                   "mbm_wta_fast_kernel evaluating all levels (profiles/<round>_ncu_kernelB_summary.txt); C3_screened_per_frame = mbm_screen_kernel + "
+                   "mbm_wta_fast_kernel behind the screen (<round>_ncu_screen_summary.txt, <round>_ncu_kernelB_screened_summary.txt); bench.py scales it by "
                    "the frames per launch"},
           open(os.path.join(P, "kernelB_traffic.json"), "w"))
 print("kernel B DRAM bytes per frame:", t / 8, "screened:", ts / 8)
