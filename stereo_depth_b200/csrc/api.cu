@@ -17,6 +17,8 @@ using namespace sd;
 namespace {
 constexpr int kSlots = 4;  // host pipeline depth (H2D / compute / D2H in flight)
 constexpr double kScreenGiveUp = 0.70;  // evaluated fraction above which the screen costs more than it saves
+constexpr double kScreenGiveUpGather = 0.40;  // the same in reference-compat mode, where a second (gather) pass of about the
+                                              // same density follows and the alternative only adds the volume stores
 constexpr int kScreenPause = 32;        // chunks without the screen before it is probed again
 constexpr size_t kGuardBytes = 64 << 10;  // per side, debug guard bands
 constexpr unsigned char kGuardPattern = 0xA5;
@@ -307,7 +309,8 @@ int run_chunk(sd_handle *h, const void *left, const void *right, int dtype, int 
             const unsigned long long w = *(volatile unsigned long long *)h->stats_host;   // [tag:16][screened:24][flagged:24]
             if (w != h->stats_seen) {
                 const double flagged = (double)(w & 0xffffffull), screened = (double)((w >> 24) & 0xffffffull);
-                if (screened > 0 && flagged > kScreenGiveUp * screened) h->screen_pause = kScreenPause;
+                const double give_up = h->s.agg_vol ? kScreenGiveUpGather : kScreenGiveUp;
+                if (screened > 0 && flagged > give_up * screened) h->screen_pause = kScreenPause;
                 h->stats_seen = w;
             }
             if (h->screen_pause > 0) {

@@ -53,14 +53,16 @@ __host__ __device__ inline size_t smem_bytes(int L, int min_ds) {
 
 // STORE: 0 nothing, 1 the whole aggregated volume (plane-major), 2 GATHER: no WTA at all, the flagged pairs' values go
 // to the compact per-tile volume (Geom::abs_index == 2) and wta4 / edge2 are left untouched.
-template <int BH, bool DBG, int MODE, int STORE>
+// SPLIT: level split (n_split_arg > 1 parts per tile); false compiles the part logic away (n_split == 1).
+template <int BH, bool DBG, int MODE, int STORE, bool SPLIT>
 __global__ void __launch_bounds__(Cfg<BH>::NT, (BH <= 32) ? 2 : 1)
 mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const float *__restrict__ padr,
                     float4 *__restrict__ wta4, float2 *__restrict__ edge2, float *__restrict__ dbg_cost,
                     float *__restrict__ dbg_agg, float *__restrict__ agg_planes, const unsigned *__restrict__ pass_mask,
                     const int *__restrict__ range_flag, int range_epoch, const int *__restrict__ tile_order,
-                    const int *__restrict__ bucket_count, int n_split, int2 *__restrict__ part_range) {
+                    const int *__restrict__ bucket_count, int n_split_arg, int2 *__restrict__ part_range) {
     using C = Cfg<BH>;
+    const int n_split = SPLIT ? n_split_arg : 1;
     extern __shared__ float4 smem4[];
     float4 *plane = smem4;                                              // [PRW][42] chunks of (cell,level) pairs
     float *bandL = reinterpret_cast<float *>(plane + C::PRW * NCHUNK);  // [BR][LW]
@@ -173,8 +175,10 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
         // overwrites: the reference's arg-max d* is always evaluated together with d*-1 and d*+1 (circular), and
         // adjacent flagged pairs that fall into different parts are joined by merge_parts_kernel.
         if (!((s_pass[(m >> 5) & 3] >> (m & 31)) & 1u)) continue;
-        if (rank++ < r_begin) continue;
-        if (rank > r_end) break;
+        if (SPLIT || STORE == 2) {
+            if (rank++ < r_begin) continue;
+            if (rank > r_end) break;
+        }
         const bool first_pass = (m_first < 0);
         if (first_pass) m_first = m;
         m_last = m;
@@ -549,11 +553,11 @@ cudaError_t launch_t(const Geom &g, int frames, const Scratch &s, float *dbg_cos
     const size_t smem = smem_bytes<BH>(g.L, g.min_ds);
     const PadGeom pg = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
     // per-device attribute: set on every launch (cheap) so multi-GPU processes stay correct
-    cudaError_t e = cudaFuncSetAttribute(mbm_wta_fast_kernel<BH, DBG, MODE, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mbm_wta_fast_kernel<BH, DBG, MODE, STORE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((g.Wd + BW - 1) / BW, (g.Hd + BH - 1) / BH, frames);
     if (STORE == 2) {
-        mbm_wta_fast_kernel<BH, DBG, MODE, STORE><<<grid, Cfg<BH>::NT, smem, st>>>(
+        mbm_wta_fast_kernel<BH, DBG, MODE, STORE, false><<<grid, Cfg<BH>::NT, smem, st>>>(
             g, pg, s.padl, s.padr, s.wta4, s.edge2, nullptr, nullptr, s.agg_vol, s.gather_mask, s.range_flag, s.range_epoch,
             nullptr, s.bucket_count, 1, nullptr);
         return cudaGetLastError();
@@ -562,7 +566,9 @@ cudaError_t launch_t(const Geom &g, int frames, const Scratch &s, float *dbg_cos
         // level split: every tile's flagged level pairs are spread over `split` blocks writing part slots, then merged
         if (STORE != 0 || DBG || !s.wta4_parts || !s.edge2_parts || !s.part_range) return cudaErrorNotSupported;
         grid.z = frames * split;
-        mbm_wta_fast_kernel<BH, DBG, MODE, STORE><<<grid, Cfg<BH>::NT, smem, st>>>(
+        e = cudaFuncSetAttribute(mbm_wta_fast_kernel<BH, false, MODE, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        mbm_wta_fast_kernel<BH, false, MODE, 0, true><<<grid, Cfg<BH>::NT, smem, st>>>(
             g, pg, s.padl, s.padr, s.wta4_parts, s.edge2_parts, nullptr, nullptr, nullptr, use_screen ? s.pass_mask : nullptr,
             s.range_flag, s.range_epoch, use_screen ? s.tile_order : nullptr, s.bucket_count, split, s.part_range);
         e = cudaGetLastError();
@@ -572,7 +578,7 @@ cudaError_t launch_t(const Geom &g, int frames, const Scratch &s, float *dbg_cos
                                                                       g.Hd, g.Wd, frames, split, pg.tiles_x, pg.tiles_y);
         return cudaGetLastError();
     }
-    mbm_wta_fast_kernel<BH, DBG, MODE, STORE><<<grid, Cfg<BH>::NT, smem, st>>>(
+    mbm_wta_fast_kernel<BH, DBG, MODE, STORE, false><<<grid, Cfg<BH>::NT, smem, st>>>(
         g, pg, s.padl, s.padr, s.wta4, s.edge2, dbg_cost, dbg_agg, s.agg_vol, use_screen ? s.pass_mask : nullptr,
         s.range_flag, s.range_epoch, use_screen ? s.tile_order : nullptr, s.bucket_count, 1, nullptr);
     return cudaGetLastError();
