@@ -450,7 +450,9 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
                 }
             }
         }
-        if (first_pass) {
+        // (unsplit: only pair 0 -- behind the screen A[0] and the fallback record matter only when level 0 is a candidate;
+        //  a part slot always needs its "no maximum in this range" record and its first level's value)
+        if (SPLIT ? first_pass : (m == 0)) {
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 const int x = px0 + (k >> 2), y = py0 + (k & 3);
