@@ -109,7 +109,10 @@ int sd_set_band(sd_handle *h, int pooled_row_offset, int global_height, const fl
  *   sd_band_p2p_connect  ipc_handles: the world x 64 bytes of all ranks (exchanged by the caller, e.g. an all-gather).
  *   sd_band_p2p_compute  left_band / right_band: [3, band rows, W] of `dtype` (device); out: [band rows + 2 * halo_rows, W]
  *                        floats, rows halo_rows .. halo_rows + band rows - 1 are this rank's part of the disparity map.
- * Every rank must call sd_band_p2p_compute the same number of times (a missing peer traps after ~10 s). */
+ * Every rank must call sd_band_p2p_compute the same number of times: a wait that sees no peer for ~10 s gives up (the
+ * CUDA context stays usable) and the next sd_band_p2p_compute returns SD_ERR_CUDA with a "timed out" message.
+ * sd_destroy on such a handle is COLLECTIVE in effect: peers may still store into / read from the exported buffer, so
+ * synchronise all ranks before any of them destroys its handle (BandedStereoMatching.close() does). */
 int sd_band_p2p_init(sd_handle *h, int world, int rank, const int32_t *band_row0, int halo_rows, int dtype, void *ipc_handle_out);
 int sd_band_p2p_connect(sd_handle *h, const void *ipc_handles);
 int sd_band_p2p_compute(sd_handle *h, const void *left_band, const void *right_band, float *out, void *cuda_stream);

@@ -58,6 +58,7 @@ struct sd_handle {
         char *base;                  // my allocation
         char *peer[8];               // every rank's allocation (peer[rank] == base)
         unsigned epoch;
+        unsigned long long *timeout_host, *timeout_dev;   // mapped word a wait kernel posts {epoch, flag} to when a peer never shows up
     } p2p;
     // host pipeline (lazily created by sd_compute_host)
     bool host_ready;
@@ -587,6 +588,7 @@ int sd_destroy(sd_handle *h) {
             for (int q = 0; q < h->p2p.world; q++)
                 if (q != h->p2p.rank && h->p2p.peer[q]) cudaIpcCloseMemHandle(h->p2p.peer[q]);
             cudaFree(h->p2p.base);
+            if (h->p2p.timeout_host) cudaFreeHost(h->p2p.timeout_host);
         }
         if (h->stats_host) cudaFreeHost(h->stats_host);
         scratch_free(h, h->s.pass_mask);
@@ -720,6 +722,10 @@ int sd_band_p2p_init(sd_handle *h, int world, int rank, const int32_t *band_row0
         return fail_cuda(h, e, "sd_band_p2p_init (memset / cudaIpcGetMemHandle)");
     }
     p.peer[rank] = p.base;
+    if (cudaHostAlloc((void **)&p.timeout_host, sizeof(unsigned long long), cudaHostAllocMapped) == cudaSuccess) {
+        *p.timeout_host = 0;
+        if (cudaHostGetDevicePointer((void **)&p.timeout_dev, p.timeout_host, 0) != cudaSuccess) p.timeout_dev = nullptr;
+    }
     static_assert(sizeof(ipc) == 64, "cudaIpcMemHandle_t is 64 bytes");
     memcpy(ipc_handle_out, &ipc, sizeof(ipc));
     p.on = true;
@@ -749,6 +755,12 @@ int sd_band_p2p_compute(sd_handle *h, const void *left_band, const void *right_b
     sd_handle::P2P &p = h->p2p;
     if (!p.on || !p.connected) return fail(h, SD_ERR_BAD_ARG, "peer-memory band mode is not connected (sd_band_p2p_init / _connect)");
     if (h->chunk < 1) return fail(h, SD_ERR_SHAPE, "handle has no scratch");
+    if (p.timeout_host && *(volatile unsigned long long *)p.timeout_host != 0) {
+        const unsigned long long w = *(volatile unsigned long long *)p.timeout_host;
+        snprintf(h->err, sizeof(h->err), "row-band exchange timed out: frame %llu never received flag %llu from a peer rank "
+                 "(a rank failed or made fewer sd_band_p2p_compute calls); results since then are invalid", w >> 32, (w & 0xffffffffull) - 1);
+        return SD_ERR_CUDA;
+    }
     DeviceGuard dg(h->device);
     if (!dg.ok) return fail(h, SD_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t st = (cudaStream_t)stream;
@@ -767,7 +779,7 @@ int sd_band_p2p_compute(sd_handle *h, const void *left_band, const void *right_b
                                    halo, band_rows + 2 * halo, rows_of(prev) + 2 * halo, rows_of(next) + 2 * halo,
                                    myflags + kCtrScatter, p2p_flags(h, prev) + kFlagFromNext, p2p_flags(h, next) + kFlagFromPrev,
                                    epoch, st));
-    SD_CUDA(h, launch_wait_flags(myflags, kFlagFromPrev, 2, epoch, st));
+    SD_CUDA(h, launch_wait_flags(myflags, kFlagFromPrev, 2, epoch, p.timeout_dev, st));
     // gray + pool on the local window [top halo | band | bottom halo]
     h->g.band_x_off = 0;
     h->g.Hd_glob = g.Hd;
@@ -781,7 +793,7 @@ int sd_band_p2p_compute(sd_handle *h, const void *left_band, const void *right_b
     for (int q = 0; q < n; q++) peer_flags[q] = p2p_flags(h, q) + kFlagGray + r;
     SD_CUDA(h, launch_publish_gray(h->s.gray + (size_t)halo * W, p2p_gray(h, r, parity), (size_t)band_rows * W,
                                    myflags + kCtrPublish, peer_flags, n, epoch, st));
-    SD_CUDA(h, launch_wait_flags(myflags, kFlagGray, n, epoch, st));
+    SD_CUDA(h, launch_wait_flags(myflags, kFlagGray, n, epoch, p.timeout_dev, st));
     // matching + secondary + fill on the window; the fill reads its colour row from whichever rank owns it
     h->g.band_x_off = (p.row0[r] - halo) / g.K;
     h->g.H_glob = p.row0[n];

@@ -76,14 +76,22 @@ __global__ void __launch_bounds__(256) publish_gray_kernel(const float4 *__restr
     if (last_block_done(counter, gridDim.x) && threadIdx.x < peers.n) st_release_sys(peers.p[threadIdx.x], epoch);
 }
 
-__global__ void wait_flags_kernel(const unsigned *flags, int first, int count, unsigned epoch) {
+// A missing peer must neither hang the GPU nor poison the CUDA context: after ~10 s the waiting lane posts
+// {epoch, flag index + 1} to a mapped host word and gives up (the frame's result is then garbage); the host reports it as
+// an error on the next sd_band_p2p_compute / sd_band_p2p_status call.
+__global__ void wait_flags_kernel(const unsigned *flags, int first, int count, unsigned epoch, unsigned long long *timeout_word) {
     const int i = threadIdx.x;
     if (i < count) {
         const long long t0 = clock64();
         // epochs wrap after 2^32 frames; the signed difference keeps the comparison valid across the wrap
         while ((int)(ld_acquire_sys(flags + first + i) - epoch) < 0) {
             __nanosleep(200);
-            if (clock64() - t0 > (20ll << 30)) __trap();   // ~10 s: a missing peer must not hang the GPU
+            if (clock64() - t0 > (20ll << 30)) {
+                if (timeout_word) *reinterpret_cast<volatile unsigned long long *>(timeout_word) =
+                    ((unsigned long long)epoch << 32) | (unsigned)(first + i + 1);
+                else __trap();
+                break;
+            }
         }
     }
 }
@@ -116,8 +124,9 @@ cudaError_t launch_publish_gray(const float *src, float *dst, size_t n_floats, u
     return cudaGetLastError();
 }
 
-cudaError_t launch_wait_flags(const unsigned *flags, int first, int count, unsigned epoch, cudaStream_t st) {
-    wait_flags_kernel<<<1, 32, 0, st>>>(flags, first, count, epoch);
+cudaError_t launch_wait_flags(const unsigned *flags, int first, int count, unsigned epoch, unsigned long long *timeout_word,
+                              cudaStream_t st) {
+    wait_flags_kernel<<<1, 32, 0, st>>>(flags, first, count, epoch, timeout_word);
     return cudaGetLastError();
 }
 

@@ -153,6 +153,7 @@ cudaError_t launch_band_scatter(const void *left, const void *right, void *own_l
                                 cudaStream_t st);
 cudaError_t launch_publish_gray(const float *src, float *dst, size_t n_floats, unsigned *counter, unsigned *const *peer_flags,
                                 int n_peers, unsigned epoch, cudaStream_t st);
-cudaError_t launch_wait_flags(const unsigned *flags, int first, int count, unsigned epoch, cudaStream_t st);
+cudaError_t launch_wait_flags(const unsigned *flags, int first, int count, unsigned epoch, unsigned long long *timeout_word,
+                              cudaStream_t st);
 
 }  // namespace sd

@@ -36,6 +36,21 @@ def test_band_plan_geometry():
         BandPlan.make(64, 64, 2, 8, 0)                           # bands shorter than the halo
 
 
+def test_band_halo_follows_the_configuration():
+    """halo = max(large_mbm_radius + ncc_patch_radius + 1, ceil((K + sad_patch_radius) / K)) pooled rows."""
+    from stereo_depth_b200 import _native as N
+    from stereo_depth_b200.bands import halo_pooled_rows
+    c = N.default_config()
+    assert halo_pooled_rows(c) == HALO_POOLED == 12
+    c.large_mbm_radius, c.ncc_patch_radius = 14, 2
+    assert halo_pooled_rows(c) == 17
+    c = N.default_config()
+    c.downscale_factor, c.sad_patch_radius, c.large_mbm_radius, c.mid_mbm_radius, c.small_mbm_radius = 1, 20, 3, 2, 1
+    assert halo_pooled_rows(c) == 21          # the secondary-matching window dominates: ceil((1 + 20) / 1)
+    p = BandPlan.make(2160, 3840, 2, 4, 1, halo=17)
+    assert p.halo_rows == 34 and p.local_rows == 540 + 68 and p.pooled_row_offset == 270 - 17
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
