@@ -825,8 +825,11 @@ int sd_compute_host(sd_handle *h, const void *left, const void *right, int dtype
     // can its D2H copy); full chunks in between keep the fused kernel's wave quantisation efficient.
     // Copies of a chunk cannot overlap its own kernels, so the host path uses chunks of at most 8 frames (the
     // device path's larger default only matters for the fused kernel's wave quantisation).
-    const int hc = h->chunk < 8 ? h->chunk : 8;
-    const int edge = (hc >= 4 && n_frames >= 3 * hc) ? 2 : hc;
+    static const int env_hc = getenv("SD_HOST_CHUNK") ? atoi(getenv("SD_HOST_CHUNK")) : 0;     // tuning knobs
+    static const int env_edge = getenv("SD_HOST_EDGE") ? atoi(getenv("SD_HOST_EDGE")) : 0;
+    const int hc_want = env_hc > 0 ? env_hc : 8;
+    const int hc = h->chunk < hc_want ? h->chunk : hc_want;
+    const int edge = (hc >= 4 && n_frames >= 3 * hc) ? (env_edge > 0 ? env_edge : 2) : hc;
     int it = 0;
     // On any failure below, copies to / from the caller's host buffers may still be in flight: drain before returning.
     struct Drain {
