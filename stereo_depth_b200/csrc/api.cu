@@ -197,10 +197,10 @@ int prof_mark(sd_handle *h, cudaStream_t st) {
     return SD_OK;
 }
 
-// The level screen runs in front of the specialised kernel only: not in the debug / reference-compat modes (they need
-// every level of the volume) and not with an explicitly selected generic or warp-specialised variant.
-// In reference-compat mode (absolute-index reads, Scratch::agg_vol) the screen stays on: instead of the whole volume, a
-// gather pass then evaluates just the level pairs those reads ask for (Geom::abs_index == 2, see run_chunk).
+// The level screen runs in front of the specialised kernel only: not with debug volumes (they need every level) and not
+// with an explicitly selected generic or warp-specialised variant.  In reference-compat mode (absolute-index reads,
+// Scratch::agg_vol) the screen stays on: instead of the whole volume, a gather pass then evaluates just the level pairs
+// those reads ask for (Geom::abs_index == 2, see run_chunk).
 bool screen_allowed(const sd_handle *h) {
     return h->screen && h->s.pass_mask && h->s.padl && (h->variant == 0 || h->variant == 2) && !h->dbg_cost &&
            !h->dbg_agg && (!h->s.agg_vol || h->s.gather_mask) && mbm_screen_supported(h->g);
