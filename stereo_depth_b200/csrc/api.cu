@@ -372,11 +372,19 @@ void destroy_host_pipeline(sd_handle *h) {
     h->host_ready = false;
 }
 
+// Frames per chunk of the pipelined host path: copies of a chunk cannot overlap its own kernels, so the host path uses
+// chunks of at most 8 frames whatever the device path's chunk is (SD_HOST_CHUNK: tuning knob).
+int host_chunk(const sd_handle *h) {
+    static const int env_hc = getenv("SD_HOST_CHUNK") ? atoi(getenv("SD_HOST_CHUNK")) : 0;
+    const int want = env_hc > 0 ? env_hc : 8;
+    return h->chunk < want ? h->chunk : want;
+}
+
 int ensure_host_pipeline(sd_handle *h, int dtype) {
     if (h->host_ready && h->host_dtype == dtype) return SD_OK;
     destroy_host_pipeline(h);
-    const size_t inb = in_bytes_per_frame(h, dtype) * h->chunk;
-    const size_t outb = (size_t)h->g.H * h->g.W * sizeof(float) * h->chunk;
+    const size_t inb = in_bytes_per_frame(h, dtype) * host_chunk(h);
+    const size_t outb = (size_t)h->g.H * h->g.W * sizeof(float) * host_chunk(h);
     memset(h->din_l, 0, sizeof(h->din_l));
     memset(h->din_r, 0, sizeof(h->din_r));
     memset(h->dout, 0, sizeof(h->dout));
@@ -467,7 +475,8 @@ int sd_create(const sd_config *cfg, int device, int frames_per_launch, sd_handle
     h->per_sm_fast = per_sm_fast;
     const long long tiles_x = (g.Wd + kTileW - 1) / kTileW;
     const long long tiles_fast = tiles_x * ((g.Hd + 31) / 32), tiles_ws = tiles_x * ((g.Hd + 63) / 64);
-    const size_t per_frame = (size_t)g.H * g.W * 4 * 2 + (size_t)g.Hd * g.Wd * 60;
+    // scratch bytes per frame of a chunk (gray, pooled, records, padded planes; + the aggregated volume in reference-compat mode)
+    const size_t per_frame = (size_t)g.H * g.W * 4 * 2 + (size_t)g.Hd * g.Wd * 60 + (g.min_ds != 0 ? (size_t)g.Hd * g.Wd * g.L * 4 : 0);
     auto cost = [&](bool ws, int f) {
         const long long slots = (long long)sms * (ws ? 1 : per_sm_fast);
         const long long waves = ((ws ? tiles_ws : tiles_fast) * f + slots - 1) / slots;
@@ -479,9 +488,9 @@ int sd_create(const sd_config *cfg, int device, int frames_per_launch, sd_handle
     int best_f = 1;
     bool best_ws = false;
     for (int v = 0; v < (ws_ok ? 2 : 1); v++)
-        for (int f = 1; f <= 16; f++) {
+        for (int f = 1; f <= 32; f++) {   // (larger launches amortise the tail of the screened kernels: 5 560 -> 5 700 frames/s at C3 from 15 to 32)
             if (frames_per_launch > 0 && f != frames_per_launch) continue;
-            if (frames_per_launch <= 0 && f > 1 && (size_t)f * per_frame > ((size_t)2 << 30)) break;
+            if (frames_per_launch <= 0 && f > 1 && (size_t)f * per_frame > ((size_t)4 << 30)) break;
             const double c = cost(v == 1, f);
             if (c < best_cost * 0.995 || (c <= best_cost * 1.0001 && (v == 1) == best_ws)) {  // near-ties: larger chunk
                 if (c < best_cost) best_cost = c;
@@ -825,10 +834,8 @@ int sd_compute_host(sd_handle *h, const void *left, const void *right, int dtype
     // can its D2H copy); full chunks in between keep the fused kernel's wave quantisation efficient.
     // Copies of a chunk cannot overlap its own kernels, so the host path uses chunks of at most 8 frames (the
     // device path's larger default only matters for the fused kernel's wave quantisation).
-    static const int env_hc = getenv("SD_HOST_CHUNK") ? atoi(getenv("SD_HOST_CHUNK")) : 0;     // tuning knobs
-    static const int env_edge = getenv("SD_HOST_EDGE") ? atoi(getenv("SD_HOST_EDGE")) : 0;
-    const int hc_want = env_hc > 0 ? env_hc : 8;
-    const int hc = h->chunk < hc_want ? h->chunk : hc_want;
+    static const int env_edge = getenv("SD_HOST_EDGE") ? atoi(getenv("SD_HOST_EDGE")) : 0;   // tuning knob
+    const int hc = host_chunk(h);
     const int edge = (hc >= 4 && n_frames >= 3 * hc) ? (env_edge > 0 ? env_edge : 2) : hc;
     int it = 0;
     // On any failure below, copies to / from the caller's host buffers may still be in flight: drain before returning.
