@@ -30,7 +30,7 @@ for row in csv.DictReader(lines):
         v, u = float(row["Metric Value"].replace(",", "")), row["Metric Unit"]
         agg[row["Kernel Name"].split("(")[0][-40:]].append(v / 1e3 if u == "ns" else (v * 1e3 if u == "ms" else v))
 tot = sum(sum(v) for v in agg.values())
-out = ["ncu --metrics gpu__time_duration.sum --clock-control none -c 400, command: python bench.py --steps 2 --warmup 3 --no-extras",
+out = ["ncu --metrics gpu__time_duration.sum --clock-control none -c 400, command: python bench.py --steps 2 --warmup 3 --no-extras --repeats 1",
        "(per-launch times are cold-cache and serialised: compare SHARES with bench.py's live roofline.share_of_step)", ""]
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     out.append(f"{k:42s} launches={len(v):4d} mean={sum(v) / len(v):9.1f} us  share={sum(v) / tot:.4f}")
