@@ -404,6 +404,22 @@ def test_reference_api_semantics():
     assert torch.equal(o3, keep)
 
 
+def test_empty_batches_are_refused():
+    """An empty batch is an error on both the device and the host path (SD_ERR_SHAPE), not a silent no-op."""
+    import torch
+    from stereo_depth_b200 import backend, cuda_depth
+    H, W = 64, 96
+    be = backend.CudaStereoMatchingBackend(cuda_depth.StereoMatchingConfiguration(height=H, width=W, min_disparity=0,
+                                                                                  max_disparity=15))
+    empty = torch.empty((0, 3, H, W), dtype=torch.uint8)
+    with pytest.raises(RuntimeError, match="n_frames must be positive"):
+        be.process_batch(empty.cuda(), empty.cuda())
+    with pytest.raises(RuntimeError, match="n_frames must be positive"):
+        be.process_batch(empty, empty)
+    with pytest.raises(RuntimeError, match="differ in length"):
+        be.process_batch(torch.zeros((2, 3, H, W), dtype=torch.uint8).cuda(), torch.zeros((1, 3, H, W), dtype=torch.uint8).cuda())
+
+
 def test_profile_hook_counts_launches():
     import torch
     from stereo_depth_b200 import cuda_depth
