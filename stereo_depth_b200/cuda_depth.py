@@ -105,6 +105,8 @@ class StereoMatching:
         if left_images.shape[0] != right_images.shape[0]:
             raise RuntimeError("left and right batches differ in length")
         n = left_images.shape[0]
+        if n == 0:
+            raise RuntimeError("empty batch: n_frames must be positive")
         code = self._dtype_code(left_images, right_images)
         if out is None:
             out = torch.empty((n, self.height, self.width), dtype=torch.float32, device=self._dev())
@@ -127,6 +129,8 @@ class StereoMatching:
         n = left_images.shape[0]
         if right_images.shape[0] != n:
             raise RuntimeError("left and right batches differ in length")
+        if n == 0:
+            raise RuntimeError("empty batch: n_frames must be positive")
         code = self._dtype_code(left_images, right_images)
         if out is None:
             out = torch.empty((n, self.height, self.width), dtype=torch.float32).pin_memory()
