@@ -60,7 +60,7 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
                     float4 *__restrict__ wta4, float2 *__restrict__ edge2, float *__restrict__ dbg_cost,
                     float *__restrict__ dbg_agg, float *__restrict__ agg_planes, const unsigned *__restrict__ pass_mask,
                     const int *__restrict__ range_flag, int range_epoch, const int *__restrict__ tile_order,
-                    const int *__restrict__ bucket_count, int n_split_arg, int2 *__restrict__ part_range) {
+                    const int *__restrict__ bucket_count, int n_split_arg, int2 *__restrict__ part_range, int store_from) {
     using C = Cfg<BH>;
     const int n_split = SPLIT ? n_split_arg : 1;
     extern __shared__ float4 smem4[];
@@ -150,8 +150,9 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
     // improves, its record (d*, A[d*-1], A[d*], A[d*+1]) is (re)written to HBM/L2 -- about ln(L) times per
     // pixel -- which keeps ~50 registers free for the adder chains.  Pixels outside the image start at
     // +inf and therefore never store.
-    float best[16], prev[16];
-    unsigned pend = 0;  // bit k: record k still waits for A[d*+1] (arrives with the next pass)
+    float best[16], prev[16], pam[16];
+    unsigned pend = 0;  // bit k: pixel k's maximum sits at the odd level of the last evaluated pair; its record (with
+                        // pam[k] = A[d*-1]) is written when the next pair delivers A[d*+1], or at the end
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         const bool valid = (px0 + (k >> 2) < Hd) && (py0 + (k & 3) < Wd);
@@ -181,6 +182,7 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
         }
         const bool first_pass = (m_first < 0);
         if (first_pass) m_first = m;
+        const int m_prev = m_last;   // the pair evaluated before this one
         m_last = m;
         const int d0 = 2 * m;
         // ================= cost phase: plane[R][s] = (cost(d0), cost(d0+1)) ==========================
@@ -426,9 +428,10 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
             __syncthreads();  // everyone is done reading the plane before the next pass overwrites it
             continue;
         }
-        if (STORE == 1 && agg_planes) {
+        if (STORE == 1 && agg_planes && (m == 0 || m >= store_from)) {
             // reference-compat mode: materialise the aggregated volume, plane-major [F][L][Hd*Wd] so that the 4
-            // pixels of a thread row are one coalesced 16-byte store per level
+            // pixels of a thread row are one coalesced 16-byte store per level.  (store_from: the absolute-index reads
+            // only ever touch level 0 and the levels from min(min_ds - 1, L - min_ds) on, see launch_t.)
             float *pl0 = agg_planes + ((size_t)frame * L + d0) * np + (size_t)px0 * Wd + py0;
             const bool vec = ((Wd & 3) == 0) && (py0 + 3 < Wd);
 #pragma unroll
@@ -465,20 +468,25 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
             }
         }
         const bool has2 = (d0 + 1 < L);
-        const float fd0 = (float)d0, fd1 = (float)(d0 + 1);
+        const float fd0 = (float)d0, fdp = (float)(2 * m_prev + 1);   // fdp: level of a pending maximum (odd level of the pair before)
         unsigned npend = 0;
+        // A record is written once it is COMPLETE and still standing: a maximum at the even level of the pair has both
+        // neighbours at hand; one at the odd level waits (pend, pam = its A[d-1]) for the next evaluated pair, whose
+        // first level is its A[d+1] -- unless that level beats it, in which case nothing was ever stored for it.  On
+        // cost curves that rise over many levels (natural scenes, out-of-range disparities) this saves a 16-byte store
+        // per pixel and level.
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             const float a0 = hv[k].x, a1 = hv[k].y;
             float4 *rec = wta4 + o00 + (size_t)(k >> 2) * Wd + (k & 3);
-            if (pend & (1u << k)) rec->w = a0;  // A[d*+1] for a maximum found at d0-1
+            if ((pend & (1u << k)) && !(a0 > best[k])) *rec = make_float4(fdp, pam[k], best[k], a0);
             if (a0 > best[k]) {
                 best[k] = a0;
-                *rec = make_float4(fd0, prev[k], a0, a1);
+                if (!(has2 && a1 > a0)) *rec = make_float4(fd0, prev[k], a0, a1);
             }
             if (has2 && a1 > best[k]) {
                 best[k] = a1;
-                *rec = make_float4(fd1, a0, a1, 0.0f);
+                pam[k] = a0;
                 npend |= 1u << k;
             }
             prev[k] = has2 ? a1 : a0;
@@ -488,6 +496,9 @@ mbm_wta_fast_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const fl
     }
 
     if (STORE == 2) return;
+#pragma unroll
+    for (int k = 0; k < 16; k++)   // maxima at the very last level evaluated: A[d*+1] lies beyond (circular wrap / next part)
+        if (pend & (1u << k)) wta4[o00 + (size_t)(k >> 2) * Wd + (k & 3)] = make_float4((float)(2 * m_last + 1), pam[k], best[k], 0.0f);
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         const int x = px0 + (k >> 2), y = py0 + (k & 3);
@@ -558,10 +569,19 @@ cudaError_t launch_t(const Geom &g, int frames, const Scratch &s, float *dbg_cos
     cudaError_t e = cudaFuncSetAttribute(mbm_wta_fast_kernel<BH, DBG, MODE, STORE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((g.Wd + BW - 1) / BW, (g.Hd + BH - 1) / BH, frames);
+    // Whole-volume store (STORE == 1, reference-compat mode): which levels can secondary matching's absolute-index reads
+    // agg[..][pad_index(q, L)], q = d* + min_ds + {-1, 0, 1} (secondary_matching.cu:28-31), ever touch?  q < L: level q >=
+    // min_ds - 1;  q == L: level 0;  q > L: a negative pad_index, i.e. level 2L - q >= L - min_ds of an earlier pixel
+    // (for min_ds <= L; beyond that several pixels back, any level).  Everything below is never read: not stored.
+    int store_from = 0;
+    if (STORE == 1 && !DBG && g.abs_index && g.min_ds >= 1 && g.min_ds <= g.L) {
+        const int first_level = g.min_ds - 1 < g.L - g.min_ds ? g.min_ds - 1 : g.L - g.min_ds;
+        store_from = first_level / 2;
+    }
     if (STORE == 2) {
         mbm_wta_fast_kernel<BH, DBG, MODE, STORE, false><<<grid, Cfg<BH>::NT, smem, st>>>(
             g, pg, s.padl, s.padr, s.wta4, s.edge2, nullptr, nullptr, s.agg_vol, s.gather_mask, s.range_flag, s.range_epoch,
-            nullptr, s.bucket_count, 1, nullptr);
+            nullptr, s.bucket_count, 1, nullptr, 0);
         return cudaGetLastError();
     }
     if (split > 1) {
@@ -572,7 +592,7 @@ cudaError_t launch_t(const Geom &g, int frames, const Scratch &s, float *dbg_cos
         if (e != cudaSuccess) return e;
         mbm_wta_fast_kernel<BH, false, MODE, 0, true><<<grid, Cfg<BH>::NT, smem, st>>>(
             g, pg, s.padl, s.padr, s.wta4_parts, s.edge2_parts, nullptr, nullptr, nullptr, use_screen ? s.pass_mask : nullptr,
-            s.range_flag, s.range_epoch, use_screen ? s.tile_order : nullptr, s.bucket_count, split, s.part_range);
+            s.range_flag, s.range_epoch, use_screen ? s.tile_order : nullptr, s.bucket_count, split, s.part_range, 0);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         const size_t n = (size_t)frames * g.Hd * g.Wd;
@@ -582,7 +602,7 @@ cudaError_t launch_t(const Geom &g, int frames, const Scratch &s, float *dbg_cos
     }
     mbm_wta_fast_kernel<BH, DBG, MODE, STORE, false><<<grid, Cfg<BH>::NT, smem, st>>>(
         g, pg, s.padl, s.padr, s.wta4, s.edge2, dbg_cost, dbg_agg, s.agg_vol, use_screen ? s.pass_mask : nullptr,
-        s.range_flag, s.range_epoch, use_screen ? s.tile_order : nullptr, s.bucket_count, 1, nullptr);
+        s.range_flag, s.range_epoch, use_screen ? s.tile_order : nullptr, s.bucket_count, 1, nullptr, store_from);
     return cudaGetLastError();
 }
 

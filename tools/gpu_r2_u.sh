@@ -1,0 +1,7 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT"
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2u_pytest.log 2>&1
+echo "pytest rc=$?"; tail -4 gpurun_out/r2u_pytest.log
+python tools/exp_natural_profile.py 2>&1 | grep "75..262"
+NF=15 SCREEN=0 timeout 300 python tools/quick_bench.py REFDEFAULT fast 2>&1 | tail -1
