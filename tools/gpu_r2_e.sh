@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_multi_gpu.py tests/test_zz_reference_live.py -m gpu -x -q > gpurun_out/r2e_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/r2e_pytest.log
 tail -8 gpurun_out/r2e_pytest.log
-timeout 900 python bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r2e_bench2.json 2> gpurun_out/r2e_bench2.err
+timeout 900 python bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r2e_bench2.json 2> gpurun_out/r2e_bench2.err
 echo "bench rc=$?"
 python - <<'PY'
 import json
