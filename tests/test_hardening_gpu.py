@@ -72,7 +72,9 @@ def _images(c):
     return l, np.roll(l, -int(rng.integers(1, 6)), axis=2).copy()
 
 
-@settings(max_examples=220, deadline=None, derandomize=True,
+# SD_HYP_EXAMPLES=N runs a longer, randomly seeded soak (e.g. 3000) instead of the fixed 220 derandomised examples
+@settings(max_examples=int(os.environ.get("SD_HYP_EXAMPLES", "220")), deadline=None,
+          derandomize="SD_HYP_EXAMPLES" not in os.environ, database=None,
           suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
 @given(stereo_case())
 def test_property_every_schedule_equals_the_oracle(c):
