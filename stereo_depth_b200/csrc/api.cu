@@ -790,6 +790,9 @@ int sd_band_p2p_compute(sd_handle *h, const void *left_band, const void *right_b
                                    epoch, st));
     SD_CUDA(h, launch_wait_flags(myflags, kFlagFromPrev, 2, epoch, p.timeout_dev, st));
     // gray + pool on the local window [top halo | band | bottom halo]
+    // (h->g is the handle's own geometry and is rewritten for the two halves of every frame: a handle is not
+    //  thread-safe -- include/stereo_b200.h -- and the kernels receive Geom by value, so launches already in flight keep
+    //  the values they were given)
     h->g.band_x_off = 0;
     h->g.Hd_glob = g.Hd;
     h->g.H_glob = g.H;
