@@ -139,6 +139,11 @@ int sd_stage_pointer(sd_handle *h, int stage, int frame, const float **ptr);
  * tensors the reference materialises (buffer/device_buffer.cc:9-10).  Pass NULLs to switch off. */
 int sd_set_debug_volumes(sd_handle *h, float *cost_volume, float *aggregated_volume);
 
+/* Parity hook for the level screen: when non-NULL, mbm_screen_kernel additionally stores its APPROXIMATE aggregated
+ * costs of frame 0 of each chunk ([Hd,Wd,L] floats, d innermost, device memory), so that a test can hold the kernel's own
+ * sums against the error bound the screen relies on (header of csrc/mbm_screen.cu).  NULL switches it off. */
+int sd_set_debug_screen(sd_handle *h, float *approx_volume);
+
 /* Reference-compat switch for min_disparity != 0.  The reference's secondary matching reads the aggregated
  * volume at pad_index(ABSOLUTE disparity, L) with unchecked flat addressing (secondary_matching.cu:28-31), which
  * for min_disparity/K != 0 is a different cell than the arg-max's neighbours (an upstream bug).  on = 1 (the

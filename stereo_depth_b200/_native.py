@@ -19,7 +19,7 @@ CONFIG_FIELDS = ("height", "width", "downscale_factor", "min_disparity", "max_di
 # every symbol include/stereo_b200.h declares
 EXPORTS = ("sd_abi_version", "sd_config_default", "sd_dims", "sd_create", "sd_destroy", "sd_compute",
            "sd_compute_range", "sd_set_band", "sd_band_p2p_init", "sd_band_p2p_connect", "sd_band_p2p_compute", "sd_compute_host", "sd_get_stage", "sd_set_debug_volumes", "sd_set_compat", "sd_set_variant",
-           "sd_launches_per_call", "sd_frames_per_launch", "sd_active_variant", "sd_set_screen", "sd_screen_active", "sd_screen_stats", "sd_screen_paused", "sd_profile_enable", "sd_profile_read", "sd_profile_read_detail", "sd_metrics", "sd_point_cloud", "sd_check_guards", "sd_stage_pointer", "sd_set_level_split", "sd_level_split",
+           "sd_launches_per_call", "sd_frames_per_launch", "sd_active_variant", "sd_set_screen", "sd_screen_active", "sd_screen_stats", "sd_screen_paused", "sd_profile_enable", "sd_profile_read", "sd_profile_read_detail", "sd_metrics", "sd_point_cloud", "sd_check_guards", "sd_stage_pointer", "sd_set_debug_screen", "sd_set_level_split", "sd_level_split",
            "sd_last_error", "sd_last_cuda_error")
 
 
@@ -63,6 +63,7 @@ def lib():
     L.sd_band_p2p_compute.argtypes = [vp, vp, vp, vp, vp]
     L.sd_get_stage.argtypes = [vp, ip, ip, vp, vp]
     L.sd_set_debug_volumes.argtypes = [vp, vp, vp]
+    L.sd_set_debug_screen.argtypes = [vp, vp]
     L.sd_set_variant.argtypes = [vp, ip]
     L.sd_set_compat.argtypes = [vp, ip]
     L.sd_launches_per_call.argtypes = [vp, ip]
@@ -153,6 +154,9 @@ class Handle:
 
     def set_debug_volumes(self, cost_ptr, agg_ptr):
         self.check(lib().sd_set_debug_volumes(self._h, cost_ptr, agg_ptr))
+
+    def set_debug_screen(self, ptr):
+        self.check(lib().sd_set_debug_screen(self._h, ptr))
 
     def set_compat(self, on):
         self.check(lib().sd_set_compat(self._h, 1 if on else 0))

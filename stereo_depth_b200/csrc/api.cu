@@ -942,6 +942,13 @@ int sd_stage_pointer(sd_handle *h, int stage, int frame, const float **ptr) {
     return SD_OK;
 }
 
+int sd_set_debug_screen(sd_handle *h, float *approx_volume) {
+    if (!h) return SD_ERR_BAD_ARG;
+    if (approx_volume && !h->s.pass_mask) return fail(h, SD_ERR_UNSUPPORTED, "this configuration has no level screen");
+    h->s.dbg_screen = approx_volume;
+    return SD_OK;
+}
+
 int sd_set_debug_volumes(sd_handle *h, float *cost_volume, float *aggregated_volume) {
     if (!h) return SD_ERR_BAD_ARG;
     h->dbg_cost = cost_volume;

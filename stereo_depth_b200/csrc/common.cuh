@@ -99,6 +99,7 @@ struct Scratch {
     float *padl, *padr;  // [F][rows][pwl], [F][rows][pwr] wrap-padded pooled planes (PadGeom), NULL if unsupported
     // Certified level screen (mbm_screen.cu), all NULL when unsupported:
     unsigned *pass_mask;              // [F][tiles_y][tiles_x][4] bit m = the fused kernel must run level pair m of that tile
+    float *dbg_screen;                // parity hook: the screen's approximate aggregated costs of frame 0, [Hd][Wd][L], or NULL
     unsigned *gather_mask;            // same shape: level pairs whose aggregated values the absolute-index reads of
                                       // secondary matching need (reference-compat mode behind the screen), else NULL
     int *tile_order;                  // [kScreenBuckets][F*tiles] tile ids bucketed by flagged-pair count (heaviest bucket last)

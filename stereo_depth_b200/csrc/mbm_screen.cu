@@ -194,11 +194,14 @@ constexpr int SWPASS = 32;      // level pairs per window
 // shared-memory footprint does not grow with L and two blocks per SM fit up to L = 128.
 // (An earlier version ran several groups of 128 threads per block on disjoint level pairs and merged their sets at the
 // end; one group per block and two blocks per SM was faster: the running maxima see every pair and settle early.)
-template <typename MaskT, bool WIN>
+// DBG: additionally store the approximate aggregated costs A' of frame 0 into dbg_vol ([Hd][Wd][L], d innermost) -- the
+// parity tests check the kernel's own sums against the bound the header claims (sd_set_debug_screen).
+template <typename MaskT, bool WIN, bool DBG>
 __global__ void __launch_bounds__(SGT, 2)
 mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const float *__restrict__ padr,
                   unsigned *__restrict__ pass_mask, unsigned long long *__restrict__ stats, int *__restrict__ tile_order,
-                  int *__restrict__ bucket_count, unsigned long long *__restrict__ host_word, int epoch) {
+                  int *__restrict__ bucket_count, unsigned long long *__restrict__ host_word, int epoch,
+                  float *__restrict__ dbg_vol) {
     extern __shared__ float4 smem4[];
     float2 *bufs = reinterpret_cast<float2 *>(smem4);                   // [Y3 | Z9 | W21]
     float *bandL = reinterpret_cast<float *>(bufs + SBUF);              // [SBR][LW]
@@ -343,6 +346,17 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
 #pragma unroll
             for (int k = 0; k < 16; k++) A[k] = __fmul2_rn(A[k], __ffma2_rn(add2(add2(S[k], S[k + 1]), S[k + 2]), neg1, cmax));
         }
+        if (DBG && frame == 0 && r0 + row < Hd) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const int yy = c0 + 16 * seg + k;
+                if (yy < Wd) {
+                    float *q = dbg_vol + ((size_t)(r0 + row) * Wd + yy) * L + d0;
+                    q[0] = A[k].x;
+                    if (d0 + 1 < L) q[1] = A[k].y;
+                }
+            }
+        }
         // ---- candidate bookkeeping: the set always contains every LEVEL within kKeep of the final maximum -----------
         const bool has2 = (d0 + 1 < L);
         const MaskT bitx = m_bit<MaskT>(2 * m), bity = m_bit<MaskT>(2 * m + 1);
@@ -431,17 +445,17 @@ mbm_screen_kernel(Geom g, PadGeom pg, const float *__restrict__ padl, const floa
     }
 }
 
-template <typename MaskT, bool WIN>
+template <typename MaskT, bool WIN, bool DBG>
 cudaError_t launch_screen_t(const Geom &g, int frames, const Scratch &s, cudaStream_t st) {
     const size_t smem = WIN ? screen_smem_bytes_windowed() : screen_smem_bytes(g.L, g.min_ds, 1);
     const PadGeom pg = make_pad_geom(g.Hd, g.Wd, g.L, g.min_ds);
-    cudaError_t e = cudaFuncSetAttribute(mbm_screen_kernel<MaskT, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mbm_screen_kernel<MaskT, WIN, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(pg.tiles_x, pg.tiles_y, frames);
     e = cudaMemsetAsync(s.bucket_count, 0, kScreenCtrlInts * sizeof(int), st);
     if (e != cudaSuccess) return e;
-    mbm_screen_kernel<MaskT, WIN><<<grid, SGT, smem, st>>>(g, pg, s.padl, s.padr, s.pass_mask, s.screen_stats, s.tile_order,
-                                                       s.bucket_count, s.screen_host_word, s.range_epoch);
+    mbm_screen_kernel<MaskT, WIN, DBG><<<grid, SGT, smem, st>>>(g, pg, s.padl, s.padr, s.pass_mask, s.screen_stats, s.tile_order,
+                                                            s.bucket_count, s.screen_host_word, s.range_epoch, s.dbg_screen);
     return cudaGetLastError();
 }
 
@@ -458,8 +472,9 @@ cudaError_t launch_mbm_screen(const Geom &g, int frames, const Scratch &s, cudaS
     // larger L: the right band is staged window by window (128-bit sets).
     const int M = ((g.L + 1) & ~1) / 2;
     if (M <= 32 && 2 * (screen_smem_bytes(g.L, g.min_ds, 1) + 1024) <= 227 * 1024)
-        return launch_screen_t<unsigned long long, false>(g, frames, s, st);
-    return launch_screen_t<Mask128, true>(g, frames, s, st);
+        return s.dbg_screen ? launch_screen_t<unsigned long long, false, true>(g, frames, s, st)
+                            : launch_screen_t<unsigned long long, false, false>(g, frames, s, st);
+    return s.dbg_screen ? launch_screen_t<Mask128, true, true>(g, frames, s, st) : launch_screen_t<Mask128, true, false>(g, frames, s, st);
 }
 
 }  // namespace sd

@@ -163,6 +163,17 @@ class StereoMatching:
         self._handle.set_debug_volumes(self._dbg[0].data_ptr(), self._dbg[1].data_ptr())
         return self._dbg
 
+    def debug_screen(self, enable=True):
+        """Allocate an [Hd,Wd,L] volume that the level screen fills with its APPROXIMATE aggregated costs of frame 0."""
+        if not enable:
+            self._handle.set_debug_screen(None)
+            self._dbg_screen = None
+            return None
+        Hd, Wd, L = self.dims
+        self._dbg_screen = torch.zeros((Hd, Wd, L), dtype=torch.float32, device=self._dev())
+        self._handle.set_debug_screen(self._dbg_screen.data_ptr())
+        return self._dbg_screen
+
     def set_compat(self, on=True):
         """Reproduce (True) or fix (False) the reference's absolute-index read for min_disparity != 0."""
         self._handle.set_compat(on)
