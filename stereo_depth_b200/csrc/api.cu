@@ -576,8 +576,16 @@ int sd_set_compat(sd_handle *h, int on) {
     return SD_OK;
 }
 
+int sd_check_guards(sd_handle *h, long long *corrupted_bytes);
+
 int sd_destroy(sd_handle *h) {
     if (!h) return SD_OK;
+    if (h->guards && h->guard_allocs && !h->guard_allocs->empty()) {
+        // debug handles (SD_DEBUG_GUARDS=1) check their guard bands one last time: a whole test run can be soaked this way
+        long long bad = 0;
+        if (sd_check_guards(h, &bad) == SD_OK && bad != 0)
+            fprintf(stderr, "libstereo_b200: GUARD BANDS CORRUPTED: %lld bytes around the scratch of a %dx%d handle\n", bad, h->g.H, h->g.W);
+    }
     {
         DeviceGuard dg(h->device);
         destroy_host_pipeline(h);
